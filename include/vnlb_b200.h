@@ -1,0 +1,146 @@
+/*
+ * vnlb_b200.h -- C ABI of libvnlb_b200.so: the B200 (sm_100a) implementation of
+ * the gauenk/vnlb `vnlb.denoise` hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes; every pointer is DEVICE memory unless it is a
+ *     parameter struct (host memory, read during the call) ;
+ *   - the caller allocates every buffer, including the workspace reported by
+ *     the matching *_workspace_bytes(); the callee never allocates;
+ *   - stream-ordered and asynchronous: work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*, NULL = default stream); no entry point
+ *     synchronises the device;
+ *   - return value 0 on success, VNLB_ERR_* (< 0) otherwise;
+ *     vnlb_last_error() returns a thread-local description of the last failure;
+ *   - re-entrant per stream; one host thread per device.
+ *   - images are float32 [T,C,H,W] (C <= 4), the index codec everywhere is
+ *         ind = t*C*H*W + y*W + x
+ *     = ravelled offset of channel 0 of the patch's top-left-front corner
+ *     (reference: lib/vnlb/search_mask/mask.py:69-71, lib/vnlb/agg/comp_agg.py:119-121);
+ *   - a row of `inds` ([B,K] int64) is VALID iff none of its K entries is -1
+ *     (reference: lib/vnlb/proc_nl.py:160-177 get_valid_patches /
+ *     fill_valid_patches).  Kernels skip invalid rows on the device, which
+ *     replaces the reference's host-side row compaction.
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to the reference repository root).
+ */
+#ifndef VNLB_B200_H
+#define VNLB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VNLB_OK 0
+#define VNLB_ERR_BAD_ARG (-1)      /* null pointer, bad shape, bad parameter     */
+#define VNLB_ERR_UNSUPPORTED (-2)  /* valid request this build cannot serve      */
+#define VNLB_ERR_CUDA (-3)         /* CUDA runtime error (see vnlb_last_error)   */
+#define VNLB_ERR_WORKSPACE (-4)    /* workspace missing or too small             */
+
+#define VNLB_WINDOW_SHIFT 0 /* search window shifted to stay inside the frame (C++ VNLB) */
+#define VNLB_WINDOW_CLIP 1  /* window clipped, out-of-frame candidates dropped           */
+
+/* Parameters of the similarity search: the fields vpss.exec_sim_search_burst
+ * reads from the reference's `args` (lib/vnlb/params.py:109-197 shortcuts
+ * ps, pt, w_s, nWt_f, nWt_b, npatches). */
+typedef struct {
+    int32_t ps;          /* spatial patch size  (sizePatch)                        */
+    int32_t pt;          /* temporal patch size (sizePatchTime)                    */
+    int32_t w_s;         /* spatial search window, odd (sizeSearchWindow)          */
+    int32_t nWt_f;       /* frames searched forward  (sizeSearchTimeFwd)           */
+    int32_t nWt_b;       /* frames searched backward (sizeSearchTimeBwd)           */
+    int32_t k;           /* neighbours kept (nSimilarPatches)                      */
+    int32_t dist_chnls;  /* channels entering the distance: 1 in step 1, C in step 2 */
+    int32_t window_mode; /* VNLB_WINDOW_SHIFT | VNLB_WINDOW_CLIP                   */
+} VnlbSearchParams;
+
+/* Parameters of the Bayes estimate: the fields bayes_est.denoise reads from
+ * `args` (lib/vnlb/deno/bayes_est.py:17-62). */
+typedef struct {
+    int32_t step;            /* 0 = first step, 1 = second step (args.step)          */
+    int32_t k;               /* patches per group (n)                                */
+    int32_t ps;              /* spatial patch size                                   */
+    int32_t pt;              /* temporal patch size                                  */
+    int32_t c;               /* channels; each is an independent p x p problem       */
+    int32_t rank;            /* eigenpairs kept (args.rank)                          */
+    float sigma2;            /* args.sigma2                                          */
+    float sigmab2;           /* args.sigmab2 (sigmaBasic^2)                          */
+    float thresh;            /* args.thresh (variThres)                              */
+    int32_t cov_from_basic;  /* args.cpatches == "basic"                             */
+    int32_t eig_method;      /* VNLB_EIG_*                                           */
+} VnlbBayesParams;
+
+#define VNLB_EIG_TRIDIAG 0 /* Householder tridiagonalisation + bisection + inverse iteration */
+#define VNLB_EIG_JACOBI 1  /* cyclic Jacobi in shared memory (slow, cross-check)             */
+
+const char *vnlb_last_error(void);
+int vnlb_version(void);
+
+/* rgb2yuv_cpp, lib/vnlb/utils/color.py:52-77 (out of place; src may equal dst). */
+int vnlb_rgb2yuv(const float *rgb, float *yuv, int T, int C, int H, int W, void *stream);
+/* apply_yuv2rgb, lib/vnlb/utils/color.py:31-50 (src may equal dst). */
+int vnlb_yuv2rgb(const float *yuv, float *rgb, int T, int C, int H, int W, void *stream);
+
+/* init_mask -> comp_params -> fill_mask, lib/vnlb/search_mask/mask.py:190-213,
+ * 252-288,315-358 (whole-frame case).  mask: int8 [T,H,W], fully written.
+ * Row bands [y_begin, y_end) restrict the SET pixels to rows of one partition
+ * (multi-GPU sharding; pass 0, H for the reference behaviour). */
+int vnlb_init_mask(int8_t *mask, int T, int H, int W, int ps, int pt, int proc_step,
+                   int y_begin, int y_end, void *stream);
+
+/* vpss.exec_sim_search_burst, call site lib/vnlb/search/search.py:86-89.
+ * img [T,C,H,W]; qinds int64 [Q,3] = (t,y,x) of each query's patch corner;
+ * fflow/bflow [T,2,H,W] (ch0 = dx, ch1 = dy) or both NULL for zero flow;
+ * vals float32 [Q,k], inds int64 [Q,k] written in place, ascending by
+ * (distance, candidate enumeration order t->y->x); slots that cannot be filled
+ * (fewer than k candidates) are set to +inf / -1. */
+size_t vnlb_search_workspace_bytes(int Q, const VnlbSearchParams *p);
+int vnlb_search_topk(const float *img, int T, int C, int H, int W, const int64_t *qinds, int Q,
+                     const float *fflow, const float *bflow, const VnlbSearchParams *p,
+                     float *vals, int64_t *inds, void *ws, size_t ws_bytes, void *stream);
+
+/* vpss.fill_patches, call site lib/vnlb/search/search.py:91-98.
+ * patches float32 [B,K,pt,C,ps,ps]; entries with ind == -1 are left untouched. */
+int vnlb_fill_patches(float *patches, const float *img, const int64_t *inds, int B, int K,
+                      int T, int C, int H, int W, int ps, int pt, void *stream);
+
+/* update_mask_inds + agg_boost, lib/vnlb/search_mask/mask.py:37-86,104-187:
+ * clears mask at every index of every VALID row and, if boost, at its 4
+ * spatial neighbours. */
+int vnlb_mask_update(int8_t *mask, const int64_t *inds, int B, int K, int T, int C, int H, int W,
+                     int boost, void *stream);
+
+/* exec_flat_areas, lib/vnlb/utils/flat_areas.py:16-34.  flat: uint8 [B]
+ * (0/1), written for every row (invalid rows get 0). thresh = gamma*sigma2. */
+int vnlb_flat_areas(const float *pnoisy, const int64_t *inds, uint8_t *flat, int B, int K,
+                    int C, int ps, int pt, float thresh, void *stream);
+
+/* bayes_est.denoise, lib/vnlb/deno/bayes_est.py:17-62: in place on
+ * pnoisy [B,K,pt,C,ps,ps]; pbasic (step 2) is read only (the reference
+ * re-centres it back to its input values, :52).  Rows that are not valid in
+ * `inds` ([B,K], may be NULL = all valid) are skipped.  rank_var float32 [B]
+ * (may be NULL).  flat uint8 [B] (may be NULL in step 1). */
+size_t vnlb_bayes_workspace_bytes(int B, const VnlbBayesParams *p);
+int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8_t *flat, const int64_t *inds,
+                      int B, const VnlbBayesParams *p, float *rank_var, void *ws, size_t ws_bytes,
+                      void *stream);
+
+/* agg_patches -> exec_agg_simple_numba, lib/vnlb/agg/comp_agg.py:47-60,106-138:
+ * deno[t+dt,ch,y+dy,x+dx] += patch, weights[t+dt,y+dy,x+dx] += 1 for every
+ * patch of every VALID row (uniform weight). */
+int vnlb_aggregate(const float *patches, const int64_t *inds, int B, int K, float *deno,
+                   float *weights, int T, int C, int H, int W, int ps, int pt, void *stream);
+
+/* lib/vnlb/proc_nl.py:118-125: deno /= weights where weights != 0, else
+ * deno = fill (basic in step 2, noisy in step 1). */
+int vnlb_normalize(float *deno, const float *weights, const float *fill, int T, int C, int H,
+                   int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VNLB_B200_H */

@@ -1,0 +1,300 @@
+"""Parity of the CUDA path (through the C ABI / the host mirror of the reference
+interface) against the CPU oracle and the reference-generated golden fixtures.
+Needs a B200; run with `pytest -m gpu`."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import inputs as gin
+from oracle import vnlb_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import vnlb_b200
+    return vnlb_b200
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def oargs(step, sigma=20., **over):
+    params = orc.default_params(sigma)
+    for k, v in over.items():
+        params[k] = [v, v]
+    return orc.get_args(params, 3, step)
+
+
+def gargs(vb, step, sigma=20., c=3, **over):
+    params = vb.get_params(sigma)
+    for k, v in over.items():
+        params[k] = [v, v]
+    return vb.get_args(params, c, step, DEV)
+
+
+# ---------------------------------------------------------------- colour / normalise
+def test_color_bit_exact(vb, golden_dir):
+    from vnlb_b200 import color
+    g = np.load(os.path.join(golden_dir, "color.npz"))
+    rgb = gin.color_inputs()
+    yuv = color.rgb2yuv(cu(rgb))
+    np.testing.assert_array_equal(yuv.cpu().numpy(), g["yuv"])
+    np.testing.assert_array_equal(yuv.cpu().numpy(), orc.rgb2yuv(rgb))
+    back = color.yuv2rgb(yuv.clone())
+    np.testing.assert_array_equal(back.cpu().numpy(), g["back"])
+    big = (np.random.RandomState(0).rand(3, 3, 37, 53) * 255).astype(np.float32)
+    np.testing.assert_array_equal(color.rgb2yuv(cu(big)).cpu().numpy(), orc.rgb2yuv(big))
+    np.testing.assert_array_equal(color.yuv2rgb(cu(big)).cpu().numpy(), orc.yuv2rgb(big))
+
+
+def test_normalize_bit_exact(vb):
+    from vnlb_b200 import agg
+    from vnlb_b200.utils import AttrDict
+    rs = np.random.RandomState(1)
+    deno = (rs.rand(2, 3, 9, 11) * 1000).astype(np.float32)
+    w = rs.randint(0, 5, (2, 9, 11)).astype(np.float32)
+    fill = (rs.rand(2, 3, 9, 11) * 255).astype(np.float32)
+    ref = deno.copy()
+    orc.normalize(ref, w, fill)
+    images = AttrDict(deno=cu(deno), weights=cu(w), basic=cu(fill), noisy=cu(fill * 0))
+    agg.normalize(images, SimpleNamespace(step=1))
+    np.testing.assert_array_equal(images.deno.cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------- mask
+@pytest.mark.parametrize("shape", [(3, 3, 64, 64), (4, 3, 64, 64), (5, 3, 33, 41), (2, 3, 7, 9), (20, 3, 96, 120)])
+def test_init_mask_bit_exact(vb, shape):
+    from vnlb_b200 import mask as gm
+    m, ng = gm.init_mask(shape, gargs(vb, 0), DEV)
+    ref, ngr = orc.init_mask(shape, oargs(0))
+    np.testing.assert_array_equal(m.cpu().numpy(), ref)
+    assert ng == ngr
+
+
+def test_mask_update_bit_exact(vb, golden_dir):
+    from vnlb_b200 import mask as gm
+    g = np.load(os.path.join(golden_dir, "mask_update.npz"))
+    inds, (T, C, H, W) = gin.mask_update_inputs()
+    m = torch.ones((T, H, W), dtype=torch.int8, device=DEV)
+    gm.update_mask_inds(m, cu(inds), C)
+    np.testing.assert_array_equal(m.cpu().numpy(), g["mask_after"])
+
+
+def test_mask2inds_same_draw_as_reference(vb):
+    from vnlb_b200 import mask as gm
+    mask_np, _ = orc.init_mask((3, 3, 40, 40), oargs(0))
+    torch.manual_seed(5)
+    a = gm.mask2inds(cu(mask_np), 128).cpu().numpy()
+    torch.manual_seed(5)
+    b = orc.mask2inds(mask_np, 128, lambda n: torch.randperm(n).numpy())
+    np.testing.assert_array_equal(a, b)
+
+
+# ---------------------------------------------------------------- search
+def run_search(vb, img, q, a_gpu, flows=None):
+    from vnlb_b200 import search
+    from vnlb_b200.utils import AttrDict
+    k = a_gpu.npatches
+    rows = q.shape[0] + 3
+    vals = torch.full((rows, k), float("inf"), device=DEV)
+    inds = torch.full((rows, k), -1, dtype=torch.int64, device=DEV)
+    fl = None
+    if flows is not None:
+        fl = AttrDict(fflow=cu(flows["fflow"]), bflow=cu(flows["bflow"]))
+    search.exec_sim_search_burst(cu(img), cu(q), vals, inds, fl, 20., a_gpu)
+    torch.cuda.synchronize()
+    return vals.cpu().numpy(), inds.cpu().numpy()
+
+
+def oracle_search(img, q, a, flows=None):
+    k = a.npatches
+    rows = q.shape[0] + 3
+    vals = np.full((rows, k), np.inf, np.float32)
+    inds = np.full((rows, k), -1, np.int64)
+    orc.exec_sim_search_burst(img, q, vals, inds, flows, 20., a)
+    return vals, inds
+
+
+def rand_queries(rs, T, H, W, ps, pt, n):
+    q = np.stack([rs.randint(0, T - pt + 1, n), rs.randint(0, H - ps + 1, n), rs.randint(0, W - ps + 1, n)], 1)
+    q[0] = (0, 0, 0)
+    q[1] = (T - pt, H - ps, W - ps)
+    q[2] = (0, H - ps, 0)
+    return q.astype(np.int64)
+
+
+SEARCH_CASES = [
+    # (shape, step, overrides)  -- first two: the reference test's inputs (tests/test_gpu_sim_search.py:138-152,261,466)
+    ((3, 3, 32, 32), 1, {}),
+    ((3, 3, 32, 32), 1, dict(sizePatch=3)),
+    ((3, 3, 64, 64), 0, {}),
+    ((3, 3, 64, 64), 1, {}),
+    ((16, 3, 72, 88), 0, dict(sizeSearchTimeFwd=4, sizeSearchTimeBwd=4)),     # config-3 parameters
+    ((16, 3, 72, 88), 1, {}),
+    ((5, 3, 24, 40), 1, dict(sizeSearchWindow=9, sizeSearchTimeFwd=2, sizeSearchTimeBwd=2, nSimilarPatches=20)),
+    ((4, 3, 20, 20), 0, dict(sizePatch=5, sizePatchTime=1, sizeSearchWindow=7, sizeSearchTimeFwd=1,
+                             sizeSearchTimeBwd=1, nSimilarPatches=10)),
+    ((6, 3, 48, 48), 1, dict(window_mode="clip")),
+]
+
+
+@pytest.mark.parametrize("shape,step,over", SEARCH_CASES)
+def test_search_bit_exact(vb, shape, step, over):
+    T, C, H, W = shape
+    rs = np.random.RandomState(10)
+    img = (rs.rand(T, C, H, W) * 255).astype(np.float32)
+    a_gpu = gargs(vb, step, **over)
+    oover = {k: v for k, v in over.items() if k != "window_mode"}
+    a_cpu = oargs(step, **oover)
+    q = rand_queries(rs, T, H, W, a_cpu.ps, a_cpu.pt, 24)
+    gv, gi = run_search(vb, img, q, a_gpu)
+    k = a_cpu.npatches
+    ov = np.full_like(gv, np.inf)
+    oi = np.full_like(gi, -1)
+    orc.exec_sim_search_burst(img, q, ov, oi, None, 20., a_cpu, window_mode=over.get("window_mode", "shift"))
+    np.testing.assert_array_equal(gi, oi)                      # indices bit-exact
+    np.testing.assert_array_equal(gv, ov)                      # distances bit-exact (same FP32 order, fmaf)
+    assert np.all(gi[q.shape[0]:] == -1)
+
+
+def test_search_with_flows_bit_exact(vb):
+    T, C, H, W = 9, 3, 56, 72
+    rs = np.random.RandomState(11)
+    img = (rs.rand(T, C, H, W) * 255).astype(np.float32)
+    flows = dict(fflow=((rs.rand(T, 2, H, W) - 0.5) * 9).astype(np.float32),
+                 bflow=((rs.rand(T, 2, H, W) - 0.5) * 9).astype(np.float32))
+    for step in (0, 1):
+        a_gpu, a_cpu = gargs(vb, step), oargs(step)
+        q = rand_queries(rs, T, H, W, 7, 2, 20)
+        gv, gi = run_search(vb, img, q, a_gpu, flows)
+        ov, oi = oracle_search(img, q, a_cpu, flows)
+        np.testing.assert_array_equal(gi, oi)
+        np.testing.assert_array_equal(gv, ov)
+
+
+def test_search_exact_ties_follow_enumeration_order(vb):
+    """Constant image: every distance is 0; the documented tie-break (enumeration
+    order frame -> y -> x) must be reproduced exactly."""
+    img = np.full((4, 3, 40, 40), 7.0, np.float32)
+    q = np.array([[1, 10, 12], [0, 0, 0]], np.int64)
+    for step in (0, 1):
+        gv, gi = run_search(vb, img, q, gargs(vb, step))
+        ov, oi = oracle_search(img, q, oargs(step))
+        np.testing.assert_array_equal(gi, oi)
+        assert np.all(gv[:2] == 0)
+
+
+def test_search_too_few_candidates_row_invalid(vb):
+    img = (np.random.RandomState(3).rand(2, 3, 9, 9) * 255).astype(np.float32)
+    q = np.array([[0, 1, 1]], np.int64)
+    gv, gi = run_search(vb, img, q, gargs(vb, 0))
+    ov, oi = oracle_search(img, q, oargs(0))
+    np.testing.assert_array_equal(gi, oi)
+    assert (gi[0] >= 0).sum() == 9 and np.isinf(gv[0, 9:]).all()
+
+
+def test_fill_patches_bit_exact(vb):
+    from vnlb_b200 import search
+    rs = np.random.RandomState(12)
+    T, C, H, W = 4, 3, 30, 34
+    img = (rs.rand(T, C, H, W) * 255).astype(np.float32)
+    B, K = 5, 60
+    t, y, x = rs.randint(0, T - 1, (B, K)), rs.randint(0, H - 6, (B, K)), rs.randint(0, W - 6, (B, K))
+    inds = (t * C * H * W + y * W + x).astype(np.int64)
+    inds[3, 7] = -1
+    p = torch.full((B, K, 2, 3, 7, 7), -3.0, device=DEV)
+    search.fill_patches(p, cu(img), cu(inds))
+    ref = np.full((B, K, 2, 3, 7, 7), -3.0, np.float32)
+    orc.fill_patches(ref, img, inds)
+    np.testing.assert_array_equal(p.cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------- flat / Bayes / aggregation
+def test_flat_areas(vb, golden_dir):
+    from vnlb_b200.flat_areas import exec_flat_areas
+    g = np.load(os.path.join(golden_dir, "flat.npz"))
+    x = gin.flat_inputs()
+    flat = torch.zeros(x.shape[0], dtype=torch.uint8, device=DEV)
+    exec_flat_areas(flat, cu(x), 0.2, 400.)
+    np.testing.assert_array_equal(flat.cpu().numpy().astype(bool), g["flat"])
+
+
+@pytest.mark.parametrize("eig", ["jacobi", "tridiag"])
+@pytest.mark.parametrize("step", [0, 1])
+def test_bayes_vs_oracle_and_golden(vb, golden_dir, step, eig):
+    from vnlb_b200 import deno
+    from vnlb_b200.utils import AttrDict
+    g = np.load(os.path.join(golden_dir, "bayes_step%d.npz" % (step + 1)))
+    pn, pb, flat = gin.bayes_inputs(step)
+    a = gargs(vb, step, eig_method=eig)
+    patches = AttrDict(noisy=cu(pn), basic=cu(pb), flat=cu(flat.astype(np.uint8)))
+    rank_var = deno.denoise(patches, a, "bayes")
+    out = patches.noisy.cpu().numpy()
+    ref_n, ref_b, ref_rv = orc.bayes_denoise(pn, pb, flat, oargs(step))
+    for name, ref in (("oracle", ref_n), ("golden", g["noisy"])):
+        for b in range(pn.shape[0]):
+            err = np.linalg.norm(out[b] - ref[b]) / np.linalg.norm(ref[b])
+            assert err < 1e-4, (name, b, err)                 # north star: filtered patches 1e-4 relative
+            cen = ref[b] - ref[b].mean(0, keepdims=True)
+            errc = np.linalg.norm((out[b] - ref[b])) / max(np.linalg.norm(cen), 1e-3)
+            assert errc < 2e-3, (name, b, errc)               # also relative to the centred signal
+    np.testing.assert_array_equal(patches.basic.cpu().numpy(), pb)          # basic untouched
+    np.testing.assert_allclose(rank_var.cpu().numpy(), ref_rv, rtol=1e-4)
+
+
+def test_bayes_skips_invalid_rows(vb):
+    from vnlb_b200 import deno
+    from vnlb_b200.utils import AttrDict
+    pn, pb, flat = gin.bayes_inputs(0)
+    inds = np.zeros((pn.shape[0], pn.shape[1]), np.int64)
+    inds[1, 5] = -1
+    patches = AttrDict(noisy=cu(pn), basic=cu(pb), flat=cu(flat.astype(np.uint8)))
+    deno.denoise(patches, gargs(vb, 0), "bayes", cu(inds))
+    out = patches.noisy.cpu().numpy()
+    np.testing.assert_array_equal(out[1], pn[1])
+    assert np.abs(out[0] - pn[0]).max() > 1
+
+
+def test_aggregate(vb, golden_dir):
+    from vnlb_b200 import agg
+    g = np.load(os.path.join(golden_dir, "agg.npz"))
+    p, inds, (T, C, H, W) = gin.agg_inputs()
+    deno = torch.zeros((T, C, H, W), device=DEV)
+    weights = torch.zeros((T, H, W), device=DEV)
+    agg.compute_agg_batch(deno, cu(p), cu(inds), weights, None, None, 7, 2)
+    np.testing.assert_array_equal(weights.cpu().numpy(), g["weights"])      # integer counts: exact
+    np.testing.assert_allclose(deno.cpu().numpy(), g["deno"], rtol=2e-6)    # float atomics: order only
+
+
+# ---------------------------------------------------------------- end to end
+def test_e2e_parity_schedule_vs_golden_and_oracle(vb, golden_dir):
+    """vnlb_b200.denoise(schedule='parity') on the reference's seeded run:
+    max-abs 1e-2 and PSNR within 0.02 dB (north-star tolerance)."""
+    g = np.load(os.path.join(golden_dir, "e2e.npz"))
+    e = gin.E2E
+    clean = orc.synth_video(e["T"], e["H"], e["W"], e["seed"])
+    noisy = orc.add_noise(clean, e["sigma"], e["seed"])
+    for eig in ("jacobi", "tridiag"):
+        params = vb.get_params(e["sigma"])
+        params["eig_method"] = [eig, eig]
+        torch.manual_seed(e["torch_seed"])
+        stats = {}
+        deno, basic, dt = vb.denoise(noisy, e["sigma"], schedule="parity", verbose=False, params=params, stats=stats)
+        deno, basic = deno.cpu().numpy(), basic.cpu().numpy()
+        assert np.abs(basic - g["basic"]).max() < 1e-2, eig
+        assert np.abs(deno - g["deno"]).max() < 1e-2, eig
+        ps = [orc.compute_psnrs(a, clean).mean() for a in (noisy, basic, deno)]
+        np.testing.assert_allclose(ps, g["psnrs"], atol=0.02)
+        ostats = {}
+        torch.manual_seed(e["torch_seed"])
+        orc.denoise(noisy, e["sigma"], stats=ostats)
+        assert stats["ngroups"] == ostats["ngroups"]          # same processed-pixel sequence
+        assert dt > 0

@@ -1,0 +1,41 @@
+// bayes.cu -- C-ABI dispatch of the per-group Bayes estimate.
+#include "common.cuh"
+
+namespace vnlb {
+int launch_bayes_jacobi(float *pnoisy, const float *pbasic, const unsigned char *flat, const long long *inds, int B,
+                        const VnlbBayesParams *p, float *rank_var, cudaStream_t st);
+}
+
+using namespace vnlb;
+
+extern "C" size_t vnlb_bayes_workspace_bytes(int B, const VnlbBayesParams *p) {
+    (void)B;
+    (void)p;
+    return 0;
+}
+
+extern "C" int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8_t *flat, const int64_t *inds, int B,
+                                 const VnlbBayesParams *p, float *rank_var, void *ws, size_t ws_bytes, void *stream) {
+    (void)ws;
+    (void)ws_bytes;
+    VNLB_REQUIRE(pnoisy && p && B >= 0, "vnlb_bayes_filter: bad argument");
+    VNLB_REQUIRE(p->step == 0 || p->step == 1, "vnlb_bayes_filter: step must be 0 or 1");
+    VNLB_REQUIRE(p->k >= 2 && p->ps >= 1 && p->pt >= 1 && p->c >= 1, "vnlb_bayes_filter: bad patch shape");
+    VNLB_REQUIRE(p->rank >= 1, "vnlb_bayes_filter: rank must be >= 1");
+    VNLB_REQUIRE(p->sigma2 > 0.f && p->sigmab2 >= 0.f, "vnlb_bayes_filter: sigma2 must be > 0");
+    VNLB_REQUIRE(!(p->step == 1 || p->cov_from_basic) || pbasic, "vnlb_bayes_filter: basic patches required");
+    if (B == 0) return VNLB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rank_var) {
+        cudaError_t e = cudaMemsetAsync(rank_var, 0, sizeof(float) * B, st);
+        if (e != cudaSuccess) { set_error("vnlb_bayes_filter: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
+    }
+    switch (p->eig_method) {
+        case VNLB_EIG_JACOBI:
+        case VNLB_EIG_TRIDIAG:  // until the tridiagonal path lands both run the Jacobi kernel
+            return launch_bayes_jacobi(pnoisy, pbasic, flat, (const long long *)inds, B, p, rank_var, st);
+        default:
+            set_error("vnlb_bayes_filter: unknown eig_method %d", p->eig_method);
+            return VNLB_ERR_BAD_ARG;
+    }
+}

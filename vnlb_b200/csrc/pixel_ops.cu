@@ -1,0 +1,175 @@
+// pixel_ops.cu -- HBM-bound per-pixel stages: colour transforms, normalisation,
+// reference-pixel mask initialisation and the "paste trick" mask update.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vnlb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ---------------------------------------------------------------------------
+// colour.  Explicit _rn intrinsics forbid FMA contraction so the result is the
+// reference's float32 evaluation order bit for bit (lib/vnlb/utils/color.py).
+// ---------------------------------------------------------------------------
+template <bool FWD>
+__global__ void color_kernel(const float *__restrict__ src, float *__restrict__ dst, int T, long long HW) {
+    const float w0 = 0.57735026918962584f;   // 1/sqrt(3)
+    const float w1 = 0.70710678118654757f;   // 1/sqrt(2)
+    const float w2f = 1.63299316185545207f;  // 2*sqrt(2)/sqrt(3)
+    const float w2 = 0.81649658092772603f;   // sqrt(2)/sqrt(3)
+    const float w2h = 0.40824829046386302f;  // sqrt(2)/sqrt(3)/2
+    const long long n = (long long)T * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / HW, r = i - t * HW;
+        const long long o = t * 3 * HW + r;
+        const float a = src[o], b = src[o + HW], c = src[o + 2 * HW];
+        float x, y, z;
+        if (FWD) {  // color.py:52-77
+            x = __fmul_rn(w0, __fadd_rn(__fadd_rn(a, b), c));
+            y = __fmul_rn(w1, __fadd_rn(a, -c));
+            z = __fmul_rn(w2f, __fadd_rn(__fadd_rn(__fmul_rn(.25f, a), -__fmul_rn(.5f, b)), __fmul_rn(.25f, c)));
+        } else {    // color.py:31-50
+            const float ya = __fmul_rn(w0, a), ub = __fmul_rn(w1, b), vh = __fmul_rn(w2h, c);
+            x = __fadd_rn(__fadd_rn(ya, ub), vh);
+            y = __fadd_rn(ya, -__fmul_rn(w2, c));
+            z = __fadd_rn(__fadd_rn(ya, -ub), vh);
+        }
+        dst[o] = x;
+        dst[o + HW] = y;
+        dst[o + 2 * HW] = z;
+    }
+}
+
+// proc_nl.py:118-125
+__global__ void normalize_kernel(float *__restrict__ deno, const float *__restrict__ weights,
+                                 const float *__restrict__ fill, int T, int C, long long HW) {
+    const long long n = (long long)T * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / HW, r = i - t * HW;
+        const float w = weights[i];
+        for (int c = 0; c < C; ++c) {
+            const long long o = (t * C + c) * HW + r;
+            deno[o] = (w != 0.f) ? __fdiv_rn(deno[o], w) : fill[o];
+        }
+    }
+}
+
+// mask.py:315-358 restated as a per-pixel predicate (whole-frame case)
+__global__ void init_mask_kernel(int8_t *__restrict__ mask, int T, int H, int W, int end_t, int end_h,
+                                 int end_w, int step, int y_begin, int y_end) {
+    const long long n = (long long)T * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int wi = (int)(i % W);
+        const int hi = (int)((i / W) % H);
+        const int ti = (int)(i / ((long long)W * H));
+        bool set = false;
+        if (ti < end_t && hi < end_h && wi < end_w && hi >= y_begin && hi < y_end) {
+            const bool last_t = ti == end_t - 1;
+            const int phase_h = last_t ? 0 : ti;
+            const bool last_h = hi == end_h - 1;
+            if ((hi % step) == (phase_h % step) || hi == 0 || last_h) {
+                const int phase_w = last_h ? 0 : phase_h + hi / step;
+                set = (wi % step) == (phase_w % step) || wi == 0 || wi == end_w - 1;
+            }
+        }
+        mask[i] = set ? 1 : 0;
+    }
+}
+
+// mask.py:37-86,104-187: one block per row of inds
+__global__ void mask_update_kernel(int8_t *__restrict__ mask, const long long *__restrict__ inds, int K,
+                                   int T, int C, int H, int W, int boost) {
+    const long long *row = inds + (long long)blockIdx.x * K;
+    if (!row_valid_block(row, K)) return;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        int t, y, x;
+        decode_ind(row[i], H, W, C, t, y, x);
+        if (t < 0 || t >= T) continue;
+        int8_t *m = mask + (long long)t * H * W;
+        m[(long long)y * W + x] = 0;
+        if (boost) {
+            if (x > 0) m[(long long)y * W + x - 1] = 0;
+            if (x < W - 1) m[(long long)y * W + x + 1] = 0;
+            if (y < H - 1) m[(long long)(y + 1) * W + x] = 0;
+            if (y > 0) m[(long long)(y - 1) * W + x] = 0;
+        }
+    }
+}
+
+}  // namespace vnlb
+
+using namespace vnlb;
+
+extern "C" const char *vnlb_last_error(void) { return g_err; }
+extern "C" int vnlb_version(void) { return 100; }
+
+static int grid_for(long long n, int threads) {
+    long long b = (n + threads - 1) / threads;
+    long long cap = (long long)num_sms() * 8;
+    return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+extern "C" int vnlb_rgb2yuv(const float *rgb, float *yuv, int T, int C, int H, int W, void *stream) {
+    VNLB_REQUIRE(rgb && yuv && T > 0 && H > 0 && W > 0, "vnlb_rgb2yuv: bad argument");
+    VNLB_REQUIRE(C == 3, "vnlb_rgb2yuv: C must be 3 (got %d)", C);
+    const long long HW = (long long)H * W;
+    color_kernel<true><<<grid_for(T * HW, 256), 256, 0, (cudaStream_t)stream>>>(rgb, yuv, T, HW);
+    return check_launch("vnlb_rgb2yuv");
+}
+
+extern "C" int vnlb_yuv2rgb(const float *yuv, float *rgb, int T, int C, int H, int W, void *stream) {
+    VNLB_REQUIRE(rgb && yuv && T > 0 && H > 0 && W > 0, "vnlb_yuv2rgb: bad argument");
+    VNLB_REQUIRE(C == 3, "vnlb_yuv2rgb: C must be 3 (got %d)", C);
+    const long long HW = (long long)H * W;
+    color_kernel<false><<<grid_for(T * HW, 256), 256, 0, (cudaStream_t)stream>>>(yuv, rgb, T, HW);
+    return check_launch("vnlb_yuv2rgb");
+}
+
+extern "C" int vnlb_normalize(float *deno, const float *weights, const float *fill, int T, int C, int H,
+                              int W, void *stream) {
+    VNLB_REQUIRE(deno && weights && fill && T > 0 && C > 0 && H > 0 && W > 0, "vnlb_normalize: bad argument");
+    const long long HW = (long long)H * W;
+    normalize_kernel<<<grid_for(T * HW, 256), 256, 0, (cudaStream_t)stream>>>(deno, weights, fill, T, C, HW);
+    return check_launch("vnlb_normalize");
+}
+
+extern "C" int vnlb_init_mask(int8_t *mask, int T, int H, int W, int ps, int pt, int proc_step, int y_begin,
+                              int y_end, void *stream) {
+    VNLB_REQUIRE(mask && T > 0 && H > 0 && W > 0, "vnlb_init_mask: bad argument");
+    VNLB_REQUIRE(ps >= 1 && pt >= 1 && proc_step >= 1, "vnlb_init_mask: bad patch size / step");
+    VNLB_REQUIRE(T >= pt && H >= ps && W >= ps, "vnlb_init_mask: video smaller than one patch");
+    const long long n = (long long)T * H * W;
+    init_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, T, H, W, T - pt + 1, H - ps + 1,
+                                                                        W - ps + 1, proc_step, y_begin, y_end);
+    return check_launch("vnlb_init_mask");
+}
+
+extern "C" int vnlb_mask_update(int8_t *mask, const int64_t *inds, int B, int K, int T, int C, int H, int W,
+                                int boost, void *stream) {
+    VNLB_REQUIRE(mask && inds && B >= 0 && K > 0 && T > 0 && C > 0 && H > 0 && W > 0,
+                 "vnlb_mask_update: bad argument");
+    if (B == 0) return VNLB_OK;
+    mask_update_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(mask, (const long long *)inds, K, T, C, H, W, boost);
+    return check_launch("vnlb_mask_update");
+}
