@@ -27,7 +27,7 @@ struct FrameWin {  // candidate window of one frame
     int t, x0, y0, nx, ny, off;
 };
 
-struct SearchShared {
+struct alignas(16) SearchShared {
     FrameWin fw[kMaxFrames];
     int nfr;
     int ncand;
