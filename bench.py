@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- vnlb.denoise throughput (steps 1+2) in Mpx/s on synthetic video.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm
+
+Workload: BASELINE.json configs[1] -- 854x480 DAVIS-shaped synthetic RGB, 20
+frames, sigma=20, no flow -- on one GPU.  With N GPUs the video is N bands of
+480 rows stacked vertically (854 x 480N x 20; N=8 is 65.6 Mpx, the size of
+configs[4]); each rank owns one band of reference pixels, so per-GPU work is
+fixed ("weak" scaling) and the accumulators are summed with one all-reduce per
+step.  A "step" of this bench = one full vnlb.denoise call (VNLB steps 1+2).
+
+One JSON line is printed by rank 0 (see README / DESIGN.md for the keys).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vnlb.denoise Mpx/s (steps 1+2)"
+SIGMA = 20.0
+BASE = dict(T=20, H=480, W=854)
+CPU_SAMPLE = dict(T=6, H=96, W=128)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def make_video(n_gpus):
+    from vnlb_b200 import synth
+    T, H, W = BASE["T"], BASE["H"] * n_gpus, BASE["W"]
+    clean = synth.synth_video(T, H, W, 123)
+    return clean, synth.add_noise(clean, SIGMA, 123)
+
+
+def cpu_reference_run(threads=None):
+    """The reference's CPU implementation of the path (oracle port: the
+    reference's own stages restated in numpy + the C/OpenMP restatement of the
+    absent vpss search) on a bounded sample of the workload.  Returns
+    (Mpx/s, seconds, cores, sample description)."""
+    from oracle import vnlb_oracle as orc
+    import torch
+    clean, noisy = make_video(1)
+    s = CPU_SAMPLE
+    crop = np.ascontiguousarray(noisy[:s["T"], :, :s["H"], :s["W"]])
+    torch.manual_seed(123)
+    t0 = time.time()
+    orc.denoise(crop, SIGMA)
+    dt = time.time() - t0
+    px = s["T"] * s["H"] * s["W"]
+    cores = max(orc.lib().oracle_num_threads(), torch.get_num_threads())
+    desc = "top-left %dx%dx%d crop of the workload, full vnlb.denoise (steps 1+2), default_params" % (
+        s["W"], s["H"], s["T"])
+    return px / 1e6 / dt, dt, cores, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, cores, desc = cpu_reference_run()
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = float(np.mean([a for a, _ in vals]))
+    ms = float(np.mean([b for _, b in vals])) * 1e3
+    line = dict(metric=METRIC, value=v, unit="Mpx/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="854x480x20 synthetic RGB, sigma=20, no flow (BASELINE configs[1]); "
+                                     "each step = bounded sample: " + desc),
+                cpu_baseline=dict(value=v, unit="Mpx/s", cores=cores, kind="port", sample=desc),
+                e2e=dict(value=v, unit="Mpx/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import vnlb_b200
+    from vnlb_b200 import _lib, dist as vdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+    assert world == n_gpus or world == 1 and n_gpus == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    clean, noisy = make_video(n_gpus)
+    T, C, H, W = noisy.shape
+    mpx = T * H * W / 1e6
+    noisy_pin = torch.from_numpy(noisy).pin_memory()
+    noisy_dev = noisy_pin.to(device)
+    out_pin = torch.empty_like(noisy_pin).pin_memory()
+    params = vnlb_b200.get_params(SIGMA)
+
+    def call(x, stats=None):
+        if world > 1:
+            return vdist.denoise_distributed(x, SIGMA, schedule="fast", params=params, stats=stats, device=device)
+        return vnlb_b200.denoise(x, SIGMA, gpuid=local_rank, verbose=False, schedule="fast", params=params, stats=stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up ----
+    stats = {}
+    for _ in range(args.warmup):
+        call(noisy_dev, stats)
+
+    # ---- device-resident throughput (`value`) ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launches
+    result = {}
+
+    def step_dev():
+        result["deno"], result["basic"], _ = call(noisy_dev)
+
+    ms = timed(step_dev, args.steps)
+    launches = (_lib.launches - l0) // max(args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through the public API with host buffers (`e2e`) ----
+    def step_e2e():
+        d, _, _ = call(noisy_pin)
+        if rank == 0:
+            out_pin.copy_(d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---- per-stage device time -> roofline of the dominant kernel (rank 0 timing, max over ranks skipped) ----
+    _lib.timer = _lib.StageTimer()
+    st2 = {}
+    call(noisy_dev, st2)
+    stage = _lib.timer.summary()
+    _lib.timer = None
+    ngroups = [int(g) for g in st2.get("ngroups", [0, 0])]
+
+    if rank == 0:
+        hbm_peak, peak_kind = load_peaks()
+        deno = result["deno"].cpu().numpy()
+        basic = result["basic"].cpu().numpy()
+        psnr = dict(noisy=float(vnlb_b200.compute_psnrs(noisy, clean).mean()),
+                    basic=float(vnlb_b200.compute_psnrs(basic, clean).mean()),
+                    deno=float(vnlb_b200.compute_psnrs(deno, clean).mean()))
+        step_ms = sum(v["ms"] for v in stage.values())
+        dom = max(stage, key=lambda k: stage[k]["ms"]) if stage else None
+        # algorithmic work per group, k=100/60, p=98, C=3, D=294
+        per_group = {
+            "bayes": dict(bytes=(2 * 100 * 294 * 4 + 2 * 60 * 294 * 4 + 60 * 294 * 4) / 2.0,
+                          flops=(35.8e6 + 31.7e6) / 2.0),
+            "search": dict(bytes=((100 + 60) * 12 / 2.0 + 24), flops=(9477 * 98 * 3 * (1 + 3)) / 2.0),
+            "aggregate": dict(bytes=(100 + 60) / 2.0 * 294 * 4, flops=(100 + 60) / 2.0 * 392),
+            "mask_fill_flat": dict(bytes=(100 * 294 * 4 + 2 * 60 * 294 * 4 + 60 * 294 * 4) / 2.0, flops=0.),
+        }
+        roof = None
+        if dom:
+            tot_groups = sum(ngroups)
+            d = stage[dom]
+            alg_bytes = per_group[dom]["bytes"] * tot_groups
+            alg_flops = per_group[dom]["flops"] * tot_groups
+            sec = d["ms"] / 1e3
+            roof = dict(kernel=dom, bound="hbm", achieved=alg_bytes / sec / 1e9, peak=hbm_peak, unit="GB/s",
+                        frac=alg_bytes / sec / 1e9 / hbm_peak, traffic=None, peak_kind=peak_kind,
+                        launches=d["launches"], avg_launch_ms=d["ms"] / max(d["launches"], 1),
+                        share_of_step=d["ms"] / max(step_ms, 1e-9),
+                        fp32=dict(achieved_tflops=alg_flops / sec / 1e12, nominal_peak_tflops=74.4,
+                                  frac=alg_flops / sec / 1e12 / 74.4,
+                                  note="kernel is FP32-FFMA bound (SURVEY 8d); nominal 148 SM x 128 lanes x 2 x 1.965 GHz"))
+        cpu = None
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            v, dt, cores, desc = cpu_reference_run()
+            cpu = dict(value=v, unit="Mpx/s", cores=cores, kind="port", sample=desc, seconds=dt)
+        line = dict(
+            metric=METRIC, value=mpx * args.steps / (ms / 1e3), unit="Mpx/s", n_gpus=n_gpus, steps=args.steps,
+            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+            vs_baseline=None, dtype="f32", data="synthetic",
+            config=dict(workload="%dx%dx%d synthetic RGB, sigma=20, no flow (BASELINE configs[1]%s)" % (
+                W, H, T, "" if n_gpus == 1 else ", %d bands of 480 rows, one per GPU" % n_gpus),
+                params="default_params: 7x7x2 patches, 27x27 window, +-6 frames, k=100/60, rank 39",
+                schedule="fast", l2="working set (noisy+basic+accumulators %.0f MB) exceeds the 126 MB L2" % (
+                    T * H * W * 4 * 10 / 1e6)),
+            e2e=dict(value=mpx * args.steps / (ms_e2e / 1e3), unit="Mpx/s", ms_per_step=ms_e2e / args.steps,
+                     h2d_bytes_per_step=int(noisy.nbytes) * max(world, 1), d2h_bytes_per_step=int(noisy.nbytes)),
+            gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
+            stages_ms={k: round(v["ms"], 3) for k, v in stage.items()}, groups_per_step=ngroups, psnr=psnr,
+            rounds=st2.get("nrounds"))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=None, help="override frame count (debugging only)")
+    args = ap.parse_args()
+    if args.frames:
+        BASE["T"] = args.frames
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,17 @@ int vnlb_fill_patches(float *patches, const float *img, const int64_t *inds, int
 int vnlb_mask_update(int8_t *mask, const int64_t *inds, int B, int K, int T, int C, int H, int W,
                      int boost, void *stream);
 
+/* Device-side replacement of mask2inds (lib/vnlb/search_mask/mask.py:18-31) for
+ * the throughput schedule.  vnlb_count_mask adds the number of set pixels to
+ * counters[0].  vnlb_select_queries appends every set pixel whose hash-based
+ * uniform draw (seed, round) falls below `prob` to qinds (int64 [cap,3] =
+ * (t,y,x)), clears it from the mask, and adds the number drawn to counters[1];
+ * draws beyond `cap` are dropped (they stay set in the mask).  counters:
+ * uint32 [2], zeroed by the caller. */
+int vnlb_count_mask(const int8_t *mask, int T, int H, int W, uint32_t *counters, void *stream);
+int vnlb_select_queries(int8_t *mask, int T, int H, int W, double prob, uint32_t seed,
+                        uint32_t round, int64_t *qinds, int cap, uint32_t *counters, void *stream);
+
 /* exec_flat_areas, lib/vnlb/utils/flat_areas.py:16-34.  flat: uint8 [B]
  * (0/1), written for every row (invalid rows get 0). thresh = gamma*sigma2. */
 int vnlb_flat_areas(const float *pnoisy, const int64_t *inds, uint8_t *flat, int B, int K,

@@ -298,3 +298,59 @@ def test_e2e_parity_schedule_vs_golden_and_oracle(vb, golden_dir):
         orc.denoise(noisy, e["sigma"], stats=ostats)
         assert stats["ngroups"] == ostats["ngroups"]          # same processed-pixel sequence
         assert dt > 0
+
+
+# ---------------------------------------------------------------- Bayes: stress and odd shapes
+def _stress_stack(rs, n, ps, pt, scale, sigma=20., c=3, b=4):
+    p = pt * ps * ps
+    s2 = sigma * sigma
+    out = np.zeros((b, c, n, p), np.float32)
+    for g in range(b):
+        for ch in range(c):
+            basis = np.linalg.qr(rs.randn(p, 3))[0]
+            coef = rs.randn(n, 3) * np.sqrt(s2 * scale) * np.array([1., .5, .25])
+            out[g, ch] = coef @ basis.T + rs.randn(n, p) * sigma + rs.rand(1, p) * 100
+    return np.ascontiguousarray(out.reshape(b, c, n, pt, ps, ps).transpose(0, 2, 3, 1, 4, 5)).astype(np.float32)
+
+
+@pytest.mark.parametrize("scale,thresh,step", [(600., 2.7, 0), (600., 1.5, 0), (5000., 2.7, 0), (600., 0.7, 1),
+                                               (50., 0.3, 1), (0.0, 0.3, 1)])
+def test_bayes_tridiag_clustered_eigenvalues(vb, scale, thresh, step):
+    """Many (up to rank = 39) tightly clustered noise eigenvalues above the threshold."""
+    from vnlb_b200 import deno
+    from vnlb_b200.utils import AttrDict
+    rs = np.random.RandomState(int(scale) + step)
+    n = 100 if step == 0 else 60
+    pn = _stress_stack(rs, n, 7, 2, scale)
+    pb = pn.copy() if step == 1 else np.zeros_like(pn)
+    flat = np.zeros(pn.shape[0], bool)
+    a_cpu = oargs(step, variThres=thresh)
+    ref_n, _, ref_rv = orc.bayes_denoise(pn, pb, flat, a_cpu)
+    for eig in ("tridiag", "jacobi"):
+        patches = AttrDict(noisy=cu(pn), basic=cu(pb), flat=cu(flat.astype(np.uint8)))
+        rv = deno.denoise(patches, gargs(vb, step, variThres=thresh, eig_method=eig), "bayes")
+        out = patches.noisy.cpu().numpy()
+        for b in range(pn.shape[0]):
+            err = np.linalg.norm(out[b] - ref_n[b]) / np.linalg.norm(ref_n[b])
+            assert err < 1e-4, (eig, b, err)
+        np.testing.assert_allclose(rv.cpu().numpy(), ref_rv, rtol=1e-4)
+
+
+@pytest.mark.parametrize("ps,pt,k", [(3, 2, 100), (5, 1, 40), (7, 1, 100), (7, 2, 33)])
+def test_bayes_other_patch_shapes(vb, ps, pt, k):
+    from vnlb_b200 import deno
+    from vnlb_b200.utils import AttrDict
+    rs = np.random.RandomState(ps * 10 + pt)
+    pn = _stress_stack(rs, k, ps, pt, 30.)
+    rank = min(39, pt * ps * ps)
+    for step in (0, 1):
+        pb = (pn + rs.randn(*pn.shape) * 2).astype(np.float32) if step == 1 else np.zeros_like(pn)
+        flat = np.zeros(pn.shape[0], bool)
+        ref_n, _, _ = orc.bayes_denoise(pn, pb, flat, oargs(step, sizePatch=ps, sizePatchTime=pt, rank=rank,
+                                                          nSimilarPatches=k))
+        patches = AttrDict(noisy=cu(pn), basic=cu(pb), flat=cu(flat.astype(np.uint8)))
+        deno.denoise(patches, gargs(vb, step, sizePatch=ps, sizePatchTime=pt, rank=rank, nSimilarPatches=k), "bayes")
+        out = patches.noisy.cpu().numpy()
+        for b in range(pn.shape[0]):
+            err = np.linalg.norm(out[b] - ref_n[b]) / np.linalg.norm(ref_n[b])
+            assert err < 1e-4, (step, b, err)

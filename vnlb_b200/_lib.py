@@ -35,6 +35,7 @@ class BayesParams(ctypes.Structure):
 EXPORTS = [
     "vnlb_last_error", "vnlb_version", "vnlb_rgb2yuv", "vnlb_yuv2rgb", "vnlb_init_mask",
     "vnlb_search_workspace_bytes", "vnlb_search_topk", "vnlb_fill_patches", "vnlb_mask_update",
+    "vnlb_count_mask", "vnlb_select_queries",
     "vnlb_flat_areas", "vnlb_bayes_workspace_bytes", "vnlb_bayes_filter", "vnlb_aggregate",
     "vnlb_normalize",
 ]
@@ -60,6 +61,8 @@ lib.vnlb_search_topk.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, ctypes.
                                  _vp, _vp, _vp, _sz, _vp]
 lib.vnlb_fill_patches.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
 lib.vnlb_mask_update.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]
+lib.vnlb_count_mask.argtypes = [_vp, _i, _i, _i, _vp, _vp]
+lib.vnlb_select_queries.argtypes = [_vp, _i, _i, _i, ctypes.c_double, ctypes.c_uint32, ctypes.c_uint32, _vp, _i, _vp, _vp]
 lib.vnlb_flat_areas.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]
 lib.vnlb_bayes_workspace_bytes.argtypes = [_i, ctypes.POINTER(BayesParams)]
 lib.vnlb_bayes_filter.argtypes = [_vp, _vp, _vp, _vp, _i, ctypes.POINTER(BayesParams), _vp, _vp, _sz, _vp]
@@ -67,7 +70,37 @@ lib.vnlb_aggregate.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _
 lib.vnlb_normalize.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp]
 
 
+launches = 0   # C-ABI calls that enqueued one of our kernels (bench.py reports it)
+
+
+class StageTimer:
+    """Optional per-stage device timing (CUDA events on the launching stream).
+    Installed by bench.py; `None` in normal operation."""
+
+    def __init__(self):
+        self.events = {}
+
+    def start(self, name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return (name, ev)
+
+    def stop(self, tok):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self.events.setdefault(tok[0], []).append((tok[1], ev))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        return {k: dict(ms=sum(a.elapsed_time(b) for a, b in v), launches=len(v)) for k, v in self.events.items()}
+
+
+timer = None
+
+
 def check(rc, what):
+    global launches
+    launches += 1
     if rc != OK:
         msg = lib.vnlb_last_error().decode()
         if rc == ERR_BAD_ARG:

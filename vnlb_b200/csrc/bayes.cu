@@ -4,6 +4,9 @@
 namespace vnlb {
 int launch_bayes_jacobi(float *pnoisy, const float *pbasic, const unsigned char *flat, const long long *inds, int B,
                         const VnlbBayesParams *p, float *rank_var, cudaStream_t st);
+int launch_bayes_tridiag(float *pnoisy, const float *pbasic, const unsigned char *flat, const long long *inds, int B,
+                         const VnlbBayesParams *p, float *rank_var, cudaStream_t st);
+bool bayes_tridiag_supported(const VnlbBayesParams *p);
 }
 
 using namespace vnlb;
@@ -31,8 +34,11 @@ extern "C" int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8
         if (e != cudaSuccess) { set_error("vnlb_bayes_filter: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
     }
     switch (p->eig_method) {
+        case VNLB_EIG_TRIDIAG:
+            if (bayes_tridiag_supported(p))
+                return launch_bayes_tridiag(pnoisy, pbasic, flat, (const long long *)inds, B, p, rank_var, st);
+            // shapes outside the tridiagonal kernel's envelope (p > 128 or rank > 40) use the Jacobi kernel
         case VNLB_EIG_JACOBI:
-        case VNLB_EIG_TRIDIAG:  // until the tridiagonal path lands both run the Jacobi kernel
             return launch_bayes_jacobi(pnoisy, pbasic, flat, (const long long *)inds, B, p, rank_var, st);
         default:
             set_error("vnlb_bayes_filter: unknown eig_method %d", p->eig_method);

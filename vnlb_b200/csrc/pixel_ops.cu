@@ -117,6 +117,55 @@ __global__ void mask_update_kernel(int8_t *__restrict__ mask, const long long *_
     }
 }
 
+// ---------------------------------------------------------------------------
+// throughput schedule: device-side replacement of mask2inds (mask.py:18-31).
+// Every set pixel draws a hash-based uniform number; pixels below `thresh`
+// become queries of this round.  counters[0] = set pixels seen, counters[1] =
+// queries appended (may exceed cap: extras stay in the mask for a later round).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int hash3(unsigned int a, unsigned int b, unsigned int c) {
+    unsigned int h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+    h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+    return h;
+}
+
+__global__ void count_mask_kernel(const int8_t *__restrict__ mask, long long n, unsigned int *__restrict__ counters) {
+    unsigned int c = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        c += mask[i] != 0;
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&counters[0], c);
+}
+
+__global__ void select_queries_kernel(int8_t *__restrict__ mask, int T, int H, int W, unsigned int thresh,
+                                      unsigned int seed, unsigned int round, long long *__restrict__ qinds, int cap,
+                                      unsigned int *__restrict__ counters) {
+    const long long n = (long long)T * H * W;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_pad = (n + 31) / 32 * 32;  // keep warps converged for the ballot
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool sel = false;
+        if (i < n && mask[i] != 0) sel = hash3((unsigned)i, (unsigned)(i >> 32) + round, seed) <= thresh;
+        const unsigned int b = __ballot_sync(0xffffffffu, sel);
+        if (b) {
+            const int lane = threadIdx.x & 31;
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&counters[1], __popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sel) {
+                const unsigned int slot = base + __popc(b & ((1u << lane) - 1));
+                if (slot < (unsigned)cap) {
+                    const int x = (int)(i % W), y = (int)((i / W) % H), t = (int)(i / ((long long)W * H));
+                    qinds[3 * (long long)slot] = t;
+                    qinds[3 * (long long)slot + 1] = y;
+                    qinds[3 * (long long)slot + 2] = x;
+                    mask[i] = 0;  // a drawn pixel is consumed even if its row turns out invalid
+                }
+            }
+        }
+    }
+}
+
 }  // namespace vnlb
 
 using namespace vnlb;
@@ -163,6 +212,24 @@ extern "C" int vnlb_init_mask(int8_t *mask, int T, int H, int W, int ps, int pt,
     init_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, T, H, W, T - pt + 1, H - ps + 1,
                                                                         W - ps + 1, proc_step, y_begin, y_end);
     return check_launch("vnlb_init_mask");
+}
+
+extern "C" int vnlb_count_mask(const int8_t *mask, int T, int H, int W, uint32_t *counters, void *stream) {
+    VNLB_REQUIRE(mask && counters && T > 0 && H > 0 && W > 0, "vnlb_count_mask: bad argument");
+    const long long n = (long long)T * H * W;
+    count_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, counters);
+    return check_launch("vnlb_count_mask");
+}
+
+extern "C" int vnlb_select_queries(int8_t *mask, int T, int H, int W, double prob, uint32_t seed, uint32_t round,
+                                   int64_t *qinds, int cap, uint32_t *counters, void *stream) {
+    VNLB_REQUIRE(mask && qinds && counters && T > 0 && H > 0 && W > 0 && cap > 0, "vnlb_select_queries: bad argument");
+    VNLB_REQUIRE(prob >= 0.0, "vnlb_select_queries: prob must be >= 0");
+    const unsigned int thresh = prob >= 1.0 ? 0xffffffffu : (unsigned int)(prob * 4294967295.0);
+    const long long n = (long long)T * H * W;
+    select_queries_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, T, H, W, thresh, seed, round,
+                                                                             (long long *)qinds, cap, counters);
+    return check_launch("vnlb_select_queries");
 }
 
 extern "C" int vnlb_mask_update(int8_t *mask, const int64_t *inds, int B, int K, int T, int C, int H, int W,

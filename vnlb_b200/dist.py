@@ -1,0 +1,74 @@
+"""Multi-GPU VNLB: one process per GPU (torch.distributed, NCCL over NVLink).
+
+The path shards over REFERENCE PIXELS: every rank holds the whole
+video (a 1080p x 30 float32 video is 746 MB, trivial next to 180 GB of HBM) and
+owns one horizontal band of the reference-pixel lattice; it searches, filters
+and aggregates only the groups whose reference pixel lies in its band.  Groups
+of neighbouring bands overlap at the band borders (patches reach a search-window
+radius into the neighbour), so the per-step accumulators (sum image + weights)
+are summed across ranks -- the one collective of the path -- and every rank then
+normalises locally, which also gives each rank the complete `basic` image that
+step 2 searches.  Each rank runs its own greedy mask over its own band, so the
+multi-GPU output matches the single-GPU output within the PSNR tolerance
+(0.02 dB), not max-abs."""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import alloc
+from .params import get_args, get_params
+from .utils import Timer, prepare_flows
+
+
+def partition_rows(h, ps, world_size, rank):
+    """Band [y0, y1) of reference-pixel rows (valid rows are 0..h-ps) of `rank`."""
+    valid = h - ps + 1
+    y0 = (valid * rank) // world_size
+    y1 = (valid * (rank + 1)) // world_size
+    if rank == world_size - 1:
+        y1 = h
+    return y0, y1
+
+
+def allreduce_accumulators(images, group=None):
+    """Sum the aggregation accumulators over ranks (border overlap + band union)."""
+    dist.all_reduce(images.deno, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(images.weights, op=dist.ReduceOp.SUM, group=group)
+
+
+def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="default", params=None,
+                        stats=None, group=None, device=None, clean=None):
+    """vnlb.denoise over all ranks of `group`.  Every rank passes the same `noisy`
+    (host or device) and receives the full (deno, basic, seconds)."""
+    clock = Timer()
+    clock.tic()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    from .proc_nl import proc_nl
+    from .schedule import proc_nl_fast
+    step_fn = proc_nl_fast if schedule == "fast" else proc_nl
+    with torch.cuda.device(device):
+        if not torch.is_tensor(noisy):
+            noisy = torch.from_numpy(np.ascontiguousarray(noisy))
+        noisy = noisy.to(device=device, dtype=torch.float32).contiguous()
+        t, c, h, w = noisy.shape
+        params = params if params is not None else get_params(sigma, False, version)
+        dflows = prepare_flows(flows, noisy.shape, device)
+
+        def reduce_fn(images):
+            allreduce_accumulators(images, group)
+
+        basic = None
+        for step in (0, 1):
+            images = alloc.allocate_images(noisy, basic, clean)
+            args = get_args(params, c, step, device)
+            y_range = partition_rows(h, args.ps, world, rank)
+            if schedule == "fast":
+                step_fn(images, dflows, args, stats, y_range, reduce_fn)
+            else:
+                step_fn(images, dflows, args, stats, y_range, reduce_fn)
+            if step == 0:
+                basic = images["deno"].clone()
+        deno = images["deno"]
+        torch.cuda.synchronize(device)
+    return deno, basic, clock.toc()

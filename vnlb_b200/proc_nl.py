@@ -23,7 +23,7 @@ def batch_params(mask, bsize, nstreams):
     return nelems, divUp(nelems, nstreams * bsize)
 
 
-def proc_nl(images, flows, args, stats=None, y_range=None):
+def proc_nl(images, flows, args, stats=None, y_range=None, reduce_fn=None):
     """lib/vnlb/proc_nl.py:38-141 ("parity" schedule).  Mutates images.deno in place."""
     mask, ngroups = search_mask.init_mask(images.shape, args, images.device, y_range)
     patches = alloc.allocate_patches(args.patch_shape, images.clean, images.device)
@@ -44,7 +44,7 @@ def proc_nl(images, flows, args, stats=None, y_range=None):
         agg.agg_patches(patches, images, bufs, args)
         if done:
             break
-    finish_step(images, args)
+    finish_step(images, args, reduce_fn)
     if stats is not None:
         stats.setdefault("ngroups", []).append(nproc)
         stats.setdefault("nmask", []).append(nelems)
