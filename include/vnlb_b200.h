@@ -140,6 +140,19 @@ int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8_t *flat, c
                       int B, const VnlbBayesParams *p, float *rank_var, void *ws, size_t ws_bytes,
                       void *stream);
 
+/* Fusion of vpss.fill_patches (search.py:91-98) + exec_flat_areas
+ * (flat_areas.py:16-34) + bayes_est.denoise (bayes_est.py:17-62) + agg_patches
+ * (comp_agg.py:47-138) for one round of groups: patches are gathered from the
+ * (YUV) images through `inds` [B,K], filtered, and added into deno [T,C,H,W] /
+ * weights [T,H,W]; the patch stacks never reach HBM.  flat_thresh =
+ * gamma*sigma2 (used in step 2 only).  Same numerics as vnlb_bayes_filter with
+ * VNLB_EIG_TRIDIAG.  vnlb_bayes_fused_supported() tells whether the patch
+ * shape fits the kernel (p = pt*ps*ps <= 128, rank <= 40). */
+int vnlb_bayes_fused_supported(const VnlbBayesParams *p);
+int vnlb_bayes_aggregate_fused(const float *img_noisy, const float *img_basic, const int64_t *inds,
+                               int B, int T, int C, int H, int W, const VnlbBayesParams *p,
+                               float flat_thresh, float *deno, float *weights, void *stream);
+
 /* agg_patches -> exec_agg_simple_numba, lib/vnlb/agg/comp_agg.py:47-60,106-138:
  * deno[t+dt,ch,y+dy,x+dx] += patch, weights[t+dt,y+dy,x+dx] += 1 for every
  * patch of every VALID row (uniform weight). */

@@ -354,3 +354,77 @@ def test_bayes_other_patch_shapes(vb, ps, pt, k):
         for b in range(pn.shape[0]):
             err = np.linalg.norm(out[b] - ref_n[b]) / np.linalg.norm(ref_n[b])
             assert err < 1e-4, (step, b, err)
+
+
+# ---------------------------------------------------------------- fused gather + Bayes + aggregate
+@pytest.mark.parametrize("step", [0, 1])
+def test_fused_kernel_matches_staged_pipeline_and_oracle(vb, step):
+    """vnlb_bayes_aggregate_fused == fill_patches + flat + bayes + agg_patches (and == oracle)."""
+    from vnlb_b200 import agg, color, deno, search
+    from vnlb_b200.flat_areas import update_flat_patch
+    from vnlb_b200.utils import AttrDict
+    T, H, W, sigma = 5, 48, 64, 20.
+    clean = orc.synth_video(T, H, W, 7)
+    noisy = orc.add_noise(clean, sigma, 7)
+    basic = (clean + np.random.RandomState(3).randn(*clean.shape) * 3).astype(np.float32)
+    a_gpu, a_cpu = gargs(vb, step), oargs(step)
+    yn, yb = orc.rgb2yuv(noisy), orc.rgb2yuv(basic if step == 1 else np.zeros_like(noisy))
+    if step == 1:
+        yn[:, :, :12, :20] = yn[:, :, :1, :1] * 0 + 90. + yn[:, :, :12, :20] * 0.01    # a flat corner
+        yb[:, :, :12, :20] = 90.
+    rs = np.random.RandomState(5)
+    q = np.stack([rs.randint(0, T - 1, 40), rs.randint(0, H - 6, 40), rs.randint(0, W - 6, 40)], 1).astype(np.int64)
+    q[0] = (0, 0, 0)
+    k = a_cpu.npatches
+    ov = np.full((40, k), np.inf, np.float32)
+    oi = np.full((40, k), -1, np.int64)
+    orc.exec_sim_search_burst(yn if step == 0 else yb, q, ov, oi, None, sigma, a_cpu)
+    oi[7, 3] = -1                                                   # an invalid row must be skipped
+    # oracle
+    pn = np.zeros((40, k, 2, 3, 7, 7), np.float32)
+    pbk = np.zeros_like(pn)
+    orc.fill_patches(pn, yn, oi)
+    orc.fill_patches(pbk, yb, oi)
+    valid = np.all(oi != -1, 1)
+    flat = orc.exec_flat_areas(pn, a_cpu.gamma, a_cpu.sigma2) if step == 1 else np.zeros(40, bool)
+    out_n, _, _ = orc.bayes_denoise(pn[valid], pbk[valid], flat[valid], a_cpu)
+    pn[valid] = out_n
+    od = np.zeros((T, 3, H, W), np.float32)
+    ow = np.zeros((T, H, W), np.float32)
+    orc.agg_patches(od, ow, pn, oi)
+    if step == 1:
+        assert flat[valid].any() and not flat[valid].all()
+    # fused CUDA kernel
+    images = AttrDict(noisy=cu(yn), basic=cu(yb), deno=torch.zeros((T, 3, H, W), device=DEV),
+                      weights=torch.zeros((T, H, W), device=DEV))
+    deno.bayes_aggregate_fused(images, cu(oi), a_gpu)
+    fd, fw = images.deno.cpu().numpy(), images.weights.cpu().numpy()
+    np.testing.assert_array_equal(fw, ow)
+    assert np.abs(fd - od).max() <= 2e-4 * np.abs(od).max()
+    # staged CUDA pipeline
+    patches = AttrDict(noisy=torch.zeros((40, k, 2, 3, 7, 7), device=DEV), basic=torch.zeros((40, k, 2, 3, 7, 7), device=DEV),
+                       flat=torch.zeros(40, dtype=torch.uint8, device=DEV))
+    gi = cu(oi)
+    search.fill_patches(patches.noisy, images.noisy, gi)
+    search.fill_patches(patches.basic, images.basic, gi)
+    update_flat_patch(patches, a_gpu, gi)
+    deno.denoise(patches, a_gpu, "bayes", gi)
+    sd = torch.zeros((T, 3, H, W), device=DEV)
+    sw = torch.zeros((T, H, W), device=DEV)
+    agg.compute_agg_batch(sd, patches.noisy, gi, sw, None, None, 7, 2)
+    np.testing.assert_array_equal(sw.cpu().numpy(), fw)
+    assert np.abs(sd.cpu().numpy() - fd).max() <= 2e-5 * np.abs(fd).max()
+
+
+def test_e2e_fast_schedule_psnr(vb, golden_dir):
+    """The throughput schedule (fused and staged) stays within the PSNR band of the parity run."""
+    g = np.load(os.path.join(golden_dir, "e2e.npz"))
+    e = gin.E2E
+    clean = orc.synth_video(e["T"], e["H"], e["W"], e["seed"])
+    noisy = orc.add_noise(clean, e["sigma"], e["seed"])
+    for fused in (True, False):
+        params = vb.get_params(e["sigma"])
+        params["fused"] = [fused, fused]
+        deno, basic, _ = vb.denoise(noisy, e["sigma"], schedule="fast", verbose=False, params=params)
+        ps = [orc.compute_psnrs(a.cpu().numpy(), clean).mean() for a in (basic, deno)]
+        assert abs(ps[0] - g["psnrs"][1]) < 0.25 and abs(ps[1] - g["psnrs"][2]) < 0.25, (fused, ps, g["psnrs"])

@@ -7,6 +7,9 @@ int launch_bayes_jacobi(float *pnoisy, const float *pbasic, const unsigned char 
 int launch_bayes_tridiag(float *pnoisy, const float *pbasic, const unsigned char *flat, const long long *inds, int B,
                          const VnlbBayesParams *p, float *rank_var, cudaStream_t st);
 bool bayes_tridiag_supported(const VnlbBayesParams *p);
+int launch_bayes_fused(const float *img_noisy, const float *img_basic, const long long *inds, int B, int T, int H,
+                       int W, const VnlbBayesParams *p, float flat_thresh, float *deno, float *weights,
+                       cudaStream_t st);
 }
 
 using namespace vnlb;
@@ -44,4 +47,24 @@ extern "C" int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8
             set_error("vnlb_bayes_filter: unknown eig_method %d", p->eig_method);
             return VNLB_ERR_BAD_ARG;
     }
+}
+
+extern "C" int vnlb_bayes_fused_supported(const VnlbBayesParams *p) { return p && bayes_tridiag_supported(p) ? 1 : 0; }
+
+extern "C" int vnlb_bayes_aggregate_fused(const float *img_noisy, const float *img_basic, const int64_t *inds, int B,
+                                          int T, int C, int H, int W, const VnlbBayesParams *p, float flat_thresh,
+                                          float *deno, float *weights, void *stream) {
+    VNLB_REQUIRE(img_noisy && inds && p && deno && weights && B >= 0, "vnlb_bayes_aggregate_fused: null pointer");
+    VNLB_REQUIRE(T > 0 && C > 0 && H > 0 && W > 0 && C == p->c, "vnlb_bayes_aggregate_fused: bad shape");
+    VNLB_REQUIRE((long long)T * C * H * W < (1LL << 31), "vnlb_bayes_aggregate_fused: video too large for 32-bit offsets");
+    VNLB_REQUIRE(p->step == 0 || p->step == 1, "vnlb_bayes_aggregate_fused: step must be 0 or 1");
+    VNLB_REQUIRE(p->sigma2 > 0.f && p->sigmab2 >= 0.f && p->rank >= 1, "vnlb_bayes_aggregate_fused: bad parameters");
+    VNLB_REQUIRE(!(p->step == 1 || p->cov_from_basic) || img_basic, "vnlb_bayes_aggregate_fused: basic image required");
+    if (!bayes_tridiag_supported(p)) {
+        set_error("vnlb_bayes_aggregate_fused: patch shape outside the fused kernel's envelope (p <= 128, rank <= 40)");
+        return VNLB_ERR_UNSUPPORTED;
+    }
+    if (B == 0) return VNLB_OK;
+    return launch_bayes_fused(img_noisy, img_basic, (const long long *)inds, B, T, H, W, p, flat_thresh, deno, weights,
+                              (cudaStream_t)stream);
 }

@@ -30,14 +30,15 @@ class _Workspace:
     _cache = {}
 
     @classmethod
-    def get(cls, device, cap, k, pt, c, ps):
-        key = (str(device), cap, k, pt, c, ps)
+    def get(cls, device, cap, k, pt, c, ps, stacks=True):
+        key = (str(device), cap, k, pt, c, ps, stacks)
         ws = cls._cache.get(key)
         if ws is None:
             cls._cache.clear()
             ws = AttrDict()
-            ws.noisy = torch.empty((cap, k, pt, c, ps, ps), dtype=torch.float32, device=device)
-            ws.basic = torch.empty((cap, k, pt, c, ps, ps), dtype=torch.float32, device=device)
+            rows = cap if stacks else 0     # the fused kernel never materialises the patch stacks
+            ws.noisy = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
+            ws.basic = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
             ws.flat = torch.zeros((cap,), dtype=torch.uint8, device=device)
             ws.vals = torch.empty((cap, k), dtype=torch.float32, device=device)
             ws.inds = torch.empty((cap, k), dtype=torch.int64, device=device)
@@ -57,7 +58,8 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
     cap = int(args.get("fast_cap", FAST_DEFAULTS["fast_cap"]))
     seed = int(args.get("fast_seed", FAST_DEFAULTS["fast_seed"])) + 7919 * int(args.step)
     k = args.npatches
-    ws = _Workspace.get(dev, cap, k, args.pt, c, args.ps)
+    fused = bool(args.get("fused", True)) and deno.fused_supported(args, c)
+    ws = _Workspace.get(dev, cap, k, args.pt, c, args.ps, stacks=not fused)
     mask = torch.empty((t, h, w), dtype=torch.int8, device=dev)
     y0, y1 = (0, h) if y_range is None else y_range
     st = L.stream_ptr()
@@ -97,6 +99,15 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
             tm.stop(tok)
             tok = tm.start("mask_fill_flat")
         search_mask.update_mask_inds(mask, inds, c, boost=args.aggreBoost)
+        if fused:
+            if tm:
+                tm.stop(tok)
+                tok = tm.start("bayes")
+            deno.bayes_aggregate_fused(images, inds, args)
+            if tm:
+                tm.stop(tok)
+            nproc += q
+            continue
         search.fill_patches(rows.noisy, images.noisy, inds)
         if args.step == 1:
             search.fill_patches(rows.basic, images.basic, inds)
