@@ -30,8 +30,17 @@ for step in (0, 1):
         ev[1].record()
     if which == "search":
         torch.cuda.synchronize(); print("step", step, "search ms", ev[0].elapsed_time(ev[1]), "queries", q.shape[0]); continue
-    if which == "bayes":
+    if which in ("bayes", "fused"):
         search.exec_sim_search_burst(yuv, q, vals, inds, None, 20., a)
+    if which == "fused":
+        images = AttrDict(noisy=yuv, basic=yuv, deno=torch.zeros_like(yuv), weights=torch.zeros((T, H, W), device=dev))
+        for it in range(2):
+            ev[2].record()
+            deno.bayes_aggregate_fused(images, inds, a)
+            ev[3].record()
+        torch.cuda.synchronize()
+        print("step", step, "fused bayes ms", ev[2].elapsed_time(ev[3]), "rows", q.shape[0])
+        continue
     pn = torch.empty((q.shape[0], k, 2, 3, 7, 7), device=dev)
     pb = torch.empty_like(pn)
     search.fill_patches(pn, yuv, inds)

@@ -34,7 +34,7 @@ namespace vnlb {
 
 constexpr int TT = 128;  // threads per CTA
 constexpr int MR = 40;   // eigenpairs kept at most (args.rank <= MR)
-constexpr int ILP = 4;   // interleaved Sturm chains per thread
+constexpr int ILP = 1;   // Sturm chains per thread in a multisection round
 constexpr int CH = 32;   // patches staged per covariance chunk
 
 struct TriLayout {
@@ -61,6 +61,7 @@ static TriLayout tri_layout(int n, int p) {
     L.rsize = rsize;
     L.xrows = (rsize - L.oX) / L.XS;
     if (L.xrows > n) L.xrows = n;
+    if (L.xrows > TT) L.xrows = TT;                         // one or two threads per staged patch
     int o = 0;
     L.oR = o; o += rsize;
     L.oD = o; o += L.LD;
@@ -127,6 +128,56 @@ __device__ __forceinline__ float block_max(float v, float *red, int &phase) {
     __syncthreads();
     phase ^= 1;
     return fmaxf(fmaxf(r[0], r[1]), fmaxf(r[2], r[3]));
+}
+
+// Wiener filter of `rows` centred patches staged in X (pitch XS): xhat = sum_r coef_r <x, v_r> v_r + mean
+// (bayes_est.py:146-151,51).  MB = number of 8-eigenpair blocks; two threads share a patch when rows <= 64.
+template <int MB>
+__device__ __forceinline__ void filter_chunk(float *X, const float *Vt, const float *coef, const float *mean, int rows,
+                                             int p, int XS, int m, int tid) {
+    const bool two = 2 * rows <= TT;
+    const int row = two ? (tid >> 1) : tid, part = two ? (tid & 1) : 0;
+    const bool on = row < rows;
+    float *xr = X + min(row, rows - 1) * XS;
+    const int ph = two ? ((p + 1) >> 1) : p;
+    const int j0 = part * ph, j1 = min(p, j0 + ph);
+    if (MB == 0) {
+        if (on) for (int j = j0; j < j1; ++j) xr[j] = mean[j];
+        return;
+    }
+    float zc[MB > 0 ? 8 * MB : 1];
+#pragma unroll
+    for (int r = 0; r < 8 * MB; ++r) zc[r] = 0.f;
+    for (int j = j0; j < j1; ++j) {
+        const float xv = xr[j];
+        const float4 *vt = reinterpret_cast<const float4 *>(Vt + j * MR);
+#pragma unroll
+        for (int b = 0; b < MB; ++b) {
+            const float4 f = vt[2 * b], h = vt[2 * b + 1];
+            zc[8 * b + 0] = fmaf(xv, f.x, zc[8 * b + 0]); zc[8 * b + 1] = fmaf(xv, f.y, zc[8 * b + 1]);
+            zc[8 * b + 2] = fmaf(xv, f.z, zc[8 * b + 2]); zc[8 * b + 3] = fmaf(xv, f.w, zc[8 * b + 3]);
+            zc[8 * b + 4] = fmaf(xv, h.x, zc[8 * b + 4]); zc[8 * b + 5] = fmaf(xv, h.y, zc[8 * b + 5]);
+            zc[8 * b + 6] = fmaf(xv, h.z, zc[8 * b + 6]); zc[8 * b + 7] = fmaf(xv, h.w, zc[8 * b + 7]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8 * MB; ++r) {
+        if (two) zc[r] += __shfl_xor_sync(0xffffffffu, zc[r], 1);
+        zc[r] *= (r < m) ? coef[r] : 0.f;
+    }
+    for (int j = j0; j < j1; ++j) {
+        const float4 *vt = reinterpret_cast<const float4 *>(Vt + j * MR);
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int b = 0; b < MB; ++b) {
+            const float4 f = vt[2 * b], h = vt[2 * b + 1];
+            o0 = fmaf(zc[8 * b + 0], f.x, o0); o1 = fmaf(zc[8 * b + 1], f.y, o1);
+            o0 = fmaf(zc[8 * b + 2], f.z, o0); o1 = fmaf(zc[8 * b + 3], f.w, o1);
+            o0 = fmaf(zc[8 * b + 4], h.x, o0); o1 = fmaf(zc[8 * b + 5], h.y, o1);
+            o0 = fmaf(zc[8 * b + 6], h.z, o0); o1 = fmaf(zc[8 * b + 7], h.w, o1);
+        }
+        if (on) xr[j] = (o0 + o1) + mean[j];
+    }
 }
 
 template <bool FUSED>
@@ -337,24 +388,25 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
             __syncthreads();
             if (active) {
                 float *ar = A + i * LD;
+                const float nvi = -vi, nwi = -wi;
                 int j = jb;
                 for (; j + 4 < LD; j += 8) {
                     float4 a4 = *reinterpret_cast<float4 *>(ar + j);
                     float4 b4 = *reinterpret_cast<float4 *>(ar + j + 4);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j), w4 = *reinterpret_cast<const float4 *>(w + j);
                     const float4 u4 = *reinterpret_cast<const float4 *>(v + j + 4), z4 = *reinterpret_cast<const float4 *>(w + j + 4);
-                    a4.x -= fmaf(vi, w4.x, wi * v4.x); a4.y -= fmaf(vi, w4.y, wi * v4.y);
-                    a4.z -= fmaf(vi, w4.z, wi * v4.z); a4.w -= fmaf(vi, w4.w, wi * v4.w);
-                    b4.x -= fmaf(vi, z4.x, wi * u4.x); b4.y -= fmaf(vi, z4.y, wi * u4.y);
-                    b4.z -= fmaf(vi, z4.z, wi * u4.z); b4.w -= fmaf(vi, z4.w, wi * u4.w);
+                    a4.x = fmaf(nvi, w4.x, fmaf(nwi, v4.x, a4.x)); a4.y = fmaf(nvi, w4.y, fmaf(nwi, v4.y, a4.y));
+                    a4.z = fmaf(nvi, w4.z, fmaf(nwi, v4.z, a4.z)); a4.w = fmaf(nvi, w4.w, fmaf(nwi, v4.w, a4.w));
+                    b4.x = fmaf(nvi, z4.x, fmaf(nwi, u4.x, b4.x)); b4.y = fmaf(nvi, z4.y, fmaf(nwi, u4.y, b4.y));
+                    b4.z = fmaf(nvi, z4.z, fmaf(nwi, u4.z, b4.z)); b4.w = fmaf(nvi, z4.w, fmaf(nwi, u4.w, b4.w));
                     *reinterpret_cast<float4 *>(ar + j) = a4;
                     *reinterpret_cast<float4 *>(ar + j + 4) = b4;
                 }
                 if (j < LD) {
                     float4 a4 = *reinterpret_cast<float4 *>(ar + j);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j), w4 = *reinterpret_cast<const float4 *>(w + j);
-                    a4.x -= fmaf(vi, w4.x, wi * v4.x); a4.y -= fmaf(vi, w4.y, wi * v4.y);
-                    a4.z -= fmaf(vi, w4.z, wi * v4.z); a4.w -= fmaf(vi, w4.w, wi * v4.w);
+                    a4.x = fmaf(nvi, w4.x, fmaf(nwi, v4.x, a4.x)); a4.y = fmaf(nvi, w4.y, fmaf(nwi, v4.y, a4.y));
+                    a4.z = fmaf(nvi, w4.z, fmaf(nwi, v4.z, a4.z)); a4.w = fmaf(nvi, w4.w, fmaf(nwi, v4.w, a4.w));
                     *reinterpret_cast<float4 *>(ar + j) = a4;
                 }
             }
@@ -403,7 +455,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
             __syncthreads();
             const int G = (TT * ILP) / m;                 // section points per eigenvalue and round
             int rounds = 1;
-            { float res = (float)(G + 1); while (res < 6.7e7f && rounds < 12) { res *= (float)(G + 1); ++rounds; } }
+            { float res = (float)(G + 1); while (res < 1.7e7f && rounds < 14) { res *= (float)(G + 1); ++rounds; } }  // 2^24 sections
             for (int r = 0; r < rounds; ++r) {
                 for (int j = tid; j < m; j += TT) { nlo[j] = __float_as_int(blo[j]); nhi[j] = __float_as_int(bhi[j]); }
                 __syncthreads();
@@ -575,44 +627,13 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                 }
             }
             __syncthreads();
-            for (int nn = tid; nn < rows; nn += TT) {
-                float *xr = X + nn * XS;
-                float zc[MR];                             // zc[r] = coef_r * <x - mean, v_r>
-#pragma unroll
-                for (int r = 0; r < MR; ++r) zc[r] = 0.f;
-                if (m > 0) {
-                    for (int j = 0; j < p; ++j) {
-                        const float xv = xr[j];
-                        const float4 *vt = reinterpret_cast<const float4 *>(Vt + j * MR);
-#pragma unroll
-                        for (int rb = 0; rb < MR; rb += 8)
-                            if (rb < m) {
-                                const float4 f = vt[rb >> 2], h = vt[(rb >> 2) + 1];
-                                zc[rb + 0] = fmaf(xv, f.x, zc[rb + 0]); zc[rb + 1] = fmaf(xv, f.y, zc[rb + 1]);
-                                zc[rb + 2] = fmaf(xv, f.z, zc[rb + 2]); zc[rb + 3] = fmaf(xv, f.w, zc[rb + 3]);
-                                zc[rb + 4] = fmaf(xv, h.x, zc[rb + 4]); zc[rb + 5] = fmaf(xv, h.y, zc[rb + 5]);
-                                zc[rb + 6] = fmaf(xv, h.z, zc[rb + 6]); zc[rb + 7] = fmaf(xv, h.w, zc[rb + 7]);
-                            }
-                    }
-#pragma unroll
-                    for (int r = 0; r < MR; ++r) zc[r] = (r < m) ? zc[r] * coef[r] : 0.f;
-                }
-                for (int j = 0; j < p; ++j) {             // xhat = sum_r zc[r] v_r + mean   (bayes_est.py:51)
-                    float o0 = 0.f, o1 = 0.f;
-                    if (m > 0) {
-                        const float4 *vt = reinterpret_cast<const float4 *>(Vt + j * MR);
-#pragma unroll
-                        for (int rb = 0; rb < MR; rb += 8)
-                            if (rb < m) {
-                                const float4 f = vt[rb >> 2], h = vt[(rb >> 2) + 1];
-                                o0 = fmaf(zc[rb + 0], f.x, o0); o1 = fmaf(zc[rb + 1], f.y, o1);
-                                o0 = fmaf(zc[rb + 2], f.z, o0); o1 = fmaf(zc[rb + 3], f.w, o1);
-                                o0 = fmaf(zc[rb + 4], h.x, o0); o1 = fmaf(zc[rb + 5], h.y, o1);
-                                o0 = fmaf(zc[rb + 6], h.z, o0); o1 = fmaf(zc[rb + 7], h.w, o1);
-                            }
-                    }
-                    xr[j] = (o0 + o1) + mean[j];
-                }
+            switch ((m + 7) >> 3) {
+                case 0: filter_chunk<0>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                case 1: filter_chunk<1>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                case 2: filter_chunk<2>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                case 3: filter_chunk<3>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                case 4: filter_chunk<4>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                default: filter_chunk<5>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
             }
             __syncthreads();
             for (int nn = warp; nn < rows; nn += TT / 32) {
