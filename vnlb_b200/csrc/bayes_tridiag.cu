@@ -38,8 +38,10 @@ constexpr int ILP = 1;   // Sturm chains per thread in a multisection round
 constexpr int CH = 32;   // patches staged per covariance chunk
 
 struct TriLayout {
-    int p, LD, ZS, XS, n;
-    int oR, rsize, oZ, oX, xrows;  // inside R: packed reflectors at 0, Z at oZ; later Vt at 0, X at oX
+    int p, LD, XS, n;
+    int gram;                      // 1: eigen-decompose the n x n Gram matrix Y Y^T/n instead of the p x p covariance
+    int q, LDq, ZSq;               // dimension of the eigenproblem and its pitches
+    int oR, rsize, oZ, oVt, oX, xrows;  // inside R: packed reflectors at 0, Z at oZ; later (Ut at 0,) Vt at oVt, X at oX
     int oD, oE, oE2, oTau, oV, oW, oMean, oLam, oCoef, oLo, oHi, oNlo, oNhi, oRed, oPb, total;
 };
 
@@ -47,30 +49,42 @@ static TriLayout tri_layout(int n, int p) {
     TriLayout L;
     L.p = p; L.n = n;
     L.LD = (p + 3) & ~3;
-    L.ZS = p | 1;
     L.XS = L.LD + 1;
-    const int nref = ((p - 1) * p / 2 + 3) & ~3;            // packed reflectors
-    L.oX = (p * MR + 3) & ~3;                               // Vt[p][MR] occupies [0, oX)
-    L.oZ = nref > L.oX ? nref : L.oX;                       // Z must not overlap the reflectors nor Vt
-    int rsize = L.LD * L.LD;
-    if (rsize < CH * L.LD) rsize = CH * L.LD;
-    if (rsize < L.oZ + MR * L.ZS) rsize = L.oZ + MR * L.ZS;
+    // Gram trick: with fewer patches than patch dimensions the non-zero spectrum of
+    // C = Y^T Y/n equals that of G = Y Y^T/n and v = Y^T u / sqrt(n lambda); step 2 (n = 60 < p = 98).
+    L.gram = (n + 8 <= p && n >= 3) ? 1 : 0;
+    L.q = L.gram ? n : p;
+    L.LDq = (L.q + 3) & ~3;
+    L.ZSq = L.q | 1;
+    const int q = L.q;
+    const int nref = ((q - 1) * q / 2 + 3) & ~3;            // packed reflectors
+    const int ut = L.gram ? ((n * MR + 3) & ~3) : 0;        // gram: Ut[n][MR] occupies [0, ut)
+    L.oVt = ut;                                             // Vt[p][MR]
+    L.oX = ut + ((p * MR + 3) & ~3);                        // X[xrows][XS]
+    const int head = L.gram ? ut : L.oX;                    // what Z must not overlap while it is transposed
+    L.oZ = nref > head ? nref : head;
+    int rsize = L.LDq * L.LDq;
+    const int chunk = L.gram ? 32 * L.LDq : CH * L.LD;      // staging of phase 0
+    if (rsize < chunk) rsize = chunk;
+    if (rsize < L.oZ + MR * L.ZSq) rsize = L.oZ + MR * L.ZSq;
     const int want_rows = n < 32 ? n : 32;
     if (rsize < L.oX + want_rows * L.XS) rsize = L.oX + want_rows * L.XS;
+    if (rsize < L.LD * L.LD && !L.gram) rsize = L.LD * L.LD;
     rsize = (rsize + 3) & ~3;
     L.rsize = rsize;
     L.xrows = (rsize - L.oX) / L.XS;
     if (L.xrows > n) L.xrows = n;
     if (L.xrows > TT) L.xrows = TT;                         // one or two threads per staged patch
+    const int vlen = L.LD > L.LDq ? L.LD : L.LDq;
     int o = 0;
     L.oR = o; o += rsize;
-    L.oD = o; o += L.LD;
-    L.oE = o; o += L.LD;
-    L.oE2 = o; o += L.LD;
-    L.oTau = o; o += L.LD;
-    L.oV = o; o += L.LD;
-    L.oW = o; o += L.LD;
-    L.oMean = o; o += L.LD;
+    L.oD = o; o += vlen;
+    L.oE = o; o += vlen;
+    L.oE2 = o; o += vlen;
+    L.oTau = o; o += vlen;
+    L.oV = o; o += vlen;
+    L.oW = o; o += vlen;
+    L.oMean = o; o += vlen;
     L.oLam = o; o += MR;
     L.oCoef = o; o += MR;
     L.oLo = o; o += MR;
@@ -180,12 +194,51 @@ __device__ __forceinline__ void filter_chunk(float *X, const float *Vt, const fl
     }
 }
 
+// Gram trick back-mapping: thread j computes row j of Vt:  Vt[j][r] = sum_nn Yc[nn][j] * Ut[nn][r] / sqrt(n * lambda_r)
+template <int MB>
+__device__ __forceinline__ void gram_map(float *Vt, const float *Ut, const float *lam, const float *mean,
+                                         const float *src, const int *pb, bool fused, int rstride, int n, int p, int m,
+                                         int coff, int tid) {
+    if (tid >= p) return;
+    float acc[8 * MB];
+#pragma unroll
+    for (int r = 0; r < 8 * MB; ++r) acc[r] = 0.f;
+    const float mj = mean[tid];
+    const float *q = src + coff;
+    for (int nn = 0; nn < n; ++nn) {
+        const float y = q[fused ? (long long)pb[nn] : (long long)nn * rstride] - mj;
+        const float4 *ut = reinterpret_cast<const float4 *>(Ut + nn * MR);
+#pragma unroll
+        for (int b = 0; b < MB; ++b) {
+            const float4 f = ut[2 * b], h = ut[2 * b + 1];
+            acc[8 * b + 0] = fmaf(y, f.x, acc[8 * b + 0]); acc[8 * b + 1] = fmaf(y, f.y, acc[8 * b + 1]);
+            acc[8 * b + 2] = fmaf(y, f.z, acc[8 * b + 2]); acc[8 * b + 3] = fmaf(y, f.w, acc[8 * b + 3]);
+            acc[8 * b + 4] = fmaf(y, h.x, acc[8 * b + 4]); acc[8 * b + 5] = fmaf(y, h.y, acc[8 * b + 5]);
+            acc[8 * b + 6] = fmaf(y, h.z, acc[8 * b + 6]); acc[8 * b + 7] = fmaf(y, h.w, acc[8 * b + 7]);
+        }
+    }
+    float4 *vt = reinterpret_cast<float4 *>(Vt + tid * MR);
+#pragma unroll
+    for (int r = 0; r < 8 * MB; ++r) acc[r] = (r < m) ? acc[r] * rsqrtf((float)n * lam[r]) : 0.f;
+#pragma unroll
+    for (int b = 0; b < MR / 8; ++b) {
+        if (b < MB) {
+            vt[2 * b] = make_float4(acc[8 * (b < MB ? b : 0) + 0], acc[8 * (b < MB ? b : 0) + 1], acc[8 * (b < MB ? b : 0) + 2], acc[8 * (b < MB ? b : 0) + 3]);
+            vt[2 * b + 1] = make_float4(acc[8 * (b < MB ? b : 0) + 4], acc[8 * (b < MB ? b : 0) + 5], acc[8 * (b < MB ? b : 0) + 6], acc[8 * (b < MB ? b : 0) + 7]);
+        } else {
+            vt[2 * b] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vt[2 * b + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
 template <bool FUSED>
 __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
     extern __shared__ __align__(16) float sm[];
     const VnlbBayesParams &P = a.P;
     const TriLayout &L = a.L;
-    const int n = P.k, ps = P.ps, ps2 = ps * ps, p = L.p, LD = L.LD, ZS = L.ZS, XS = L.XS, C = P.c;
+    const int n = P.k, ps = P.ps, ps2 = ps * ps, p = L.p, LD = L.LD, XS = L.XS, C = P.c;
+    const int qd = L.q, LDq = L.LDq, ZSq = L.ZSq;   // eigenproblem dimension (p, or n with the Gram trick)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = FUSED ? blockIdx.x : blockIdx.x / C;
     if (a.inds && !row_valid_block(a.inds + (long long)g * n, n)) return;
@@ -267,11 +320,10 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                 for (; nn < n; ++nn) s0 += q[row_off(nn)];
             }
             mean[j] = ((s0 + s1) + (s2 + s3)) * inv_n;
-            v[j] = 0.f;
-            w[j] = 0.f;
         }
-        // lower-triangular 4x4 tiles of C owned by this thread
-        const int ntile = LD >> 2, ntri = ntile * (ntile + 1) / 2;
+        for (int j = tid; j < LDq; j += TT) { v[j] = 0.f; w[j] = 0.f; }
+        // lower-triangular 4x4 tiles of the qd x qd matrix (covariance or Gram) owned by this thread
+        const int ntile = LDq >> 2, ntri = ntile * (ntile + 1) / 2;
         int ti[3], tj[3];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
@@ -292,34 +344,65 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
 #pragma unroll
             for (int q = 0; q < 16; ++q) acc[t][q] = 0.f;
         __syncthreads();
-        for (int c0 = 0; c0 < n; c0 += CH) {
-            const int rows = min(CH, n - c0);
-            for (int nn = warp; nn < rows; nn += TT / 32) {
-                const float *q = src + row_off(c0 + nn);
+        if (!L.gram) {
+            // C = Y^T Y: patches staged 32 at a time as rows Y[nn][0..LD)
+            for (int c0 = 0; c0 < n; c0 += CH) {
+                const int rows = min(CH, n - c0);
+                for (int nn = warp; nn < rows; nn += TT / 32) {
+                    const float *q = src + row_off(c0 + nn);
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int j = lane + 32 * qq;
-                    if (j < LD) R[nn * LD + j] = (j < p) ? q[co[qq]] - mean[j] : 0.f;
-                }
-            }
-            __syncthreads();
-            for (int nn = 0; nn < rows; ++nn) {
-                const float *row = R + nn * LD;
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    if (ti[t] >= 0) {
-                        const float4 xi = *reinterpret_cast<const float4 *>(row + 4 * ti[t]);
-                        const float4 xj = *reinterpret_cast<const float4 *>(row + 4 * tj[t]);
-                        const float a4[4] = {xi.x, xi.y, xi.z, xi.w}, b4[4] = {xj.x, xj.y, xj.z, xj.w};
-#pragma unroll
-                        for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-                            for (int bb = 0; bb < 4; ++bb)
-                                acc[t][aa * 4 + bb] = fmaf(a4[aa], b4[bb], acc[t][aa * 4 + bb]);
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int j = lane + 32 * qq;
+                        if (j < LD) R[nn * LD + j] = (j < p) ? q[co[qq]] - mean[j] : 0.f;
                     }
                 }
+                __syncthreads();
+                for (int nn = 0; nn < rows; ++nn) {
+                    const float *row = R + nn * LD;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        if (ti[t] >= 0) {
+                            const float4 xi = *reinterpret_cast<const float4 *>(row + 4 * ti[t]);
+                            const float4 xj = *reinterpret_cast<const float4 *>(row + 4 * tj[t]);
+                            const float a4[4] = {xi.x, xi.y, xi.z, xi.w}, b4[4] = {xj.x, xj.y, xj.z, xj.w};
+#pragma unroll
+                            for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                                for (int bb = 0; bb < 4; ++bb)
+                                    acc[t][aa * 4 + bb] = fmaf(a4[aa], b4[bb], acc[t][aa * 4 + bb]);
+                        }
+                    }
+                }
+                __syncthreads();
             }
-            __syncthreads();
+        } else {
+            // G = Y Y^T: 32 patch-element columns at a time, staged transposed as Yt[col][0..LDq)
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const int ncol = min(32, p - 32 * qq);
+                if (ncol <= 0) break;
+                const int j = lane + 32 * qq;
+                for (int nn = warp; nn < LDq; nn += TT / 32)
+                    R[lane * LDq + nn] = (j < p && nn < n) ? src[row_off(nn) + co[qq]] - mean[j] : 0.f;
+                __syncthreads();
+                for (int l = 0; l < ncol; ++l) {
+                    const float *row = R + l * LDq;
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        if (ti[t] >= 0) {
+                            const float4 xi = *reinterpret_cast<const float4 *>(row + 4 * ti[t]);
+                            const float4 xj = *reinterpret_cast<const float4 *>(row + 4 * tj[t]);
+                            const float a4[4] = {xi.x, xi.y, xi.z, xi.w}, b4[4] = {xj.x, xj.y, xj.z, xj.w};
+#pragma unroll
+                            for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                                for (int bb = 0; bb < 4; ++bb)
+                                    acc[t][aa * 4 + bb] = fmaf(a4[aa], b4[bb], acc[t][aa * 4 + bb]);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
         }
         float *A = R;
 #pragma unroll
@@ -330,23 +413,23 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
 #pragma unroll
                     for (int bb = 0; bb < 4; ++bb) {
                         const float cval = acc[t][aa * 4 + bb] * inv_n;
-                        A[(4 * ti[t] + aa) * LD + 4 * tj[t] + bb] = cval;
-                        A[(4 * tj[t] + bb) * LD + 4 * ti[t] + aa] = cval;
+                        A[(4 * ti[t] + aa) * LDq + 4 * tj[t] + bb] = cval;
+                        A[(4 * tj[t] + bb) * LDq + 4 * ti[t] + aa] = cval;
                     }
         __syncthreads();
         {   // rank_var = mean over channels of trace(C) (bayes_est.py:39-40)
-            const float tr = block_sum(tid < p ? A[tid * LD + tid] : 0.f, red, phase);
+            const float tr = block_sum(tid < qd ? A[tid * LDq + tid] : 0.f, red, phase);
             if (a.rank_var && tid == 0) atomicAdd(&a.rank_var[g], tr / (float)C);
         }
 
         // -------------------------------------------------------------- 1. tridiagonalisation
-        for (int k = 0; k < p - 2; ++k) {
-            const int m = p - 1 - k;
+        for (int k = 0; k < qd - 2; ++k) {
+            const int m = qd - 1 - k;
             const bool active = tid < m;
             const int i = k + 1 + tid;
-            const float x = active ? A[k * LD + i] : 0.f;
-            const float dk = A[k * LD + k];
-            const float alpha = A[k * LD + k + 1];
+            const float x = active ? A[k * LDq + i] : 0.f;
+            const float dk = A[k * LDq + k];
+            const float alpha = A[k * LDq + k + 1];
             const float ssq = block_sum((active && tid > 0) ? x * x : 0.f, red, phase);
             if (ssq == 0.f) {  // nothing to annihilate
                 if (tid == 0) { d[k] = dk; e[k] = alpha; taus[k] = 0.f; v[k] = 0.f; w[k] = 0.f; }
@@ -357,16 +440,16 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
             const float scale = 1.f / (alpha - beta);
             const float vi = (tid == 0) ? 1.f : x * scale;
             // reflector k goes, packed, over the dead rows 0..k (every thread has read row k: block_sum synced)
-            if (active) { v[i] = vi; R[k * (p - 1) - (k * (k - 1)) / 2 + tid] = vi; }
+            if (active) { v[i] = vi; R[k * (qd - 1) - (k * (k - 1)) / 2 + tid] = vi; }
             if (tid == 0) { v[k] = 0.f; w[k] = 0.f; d[k] = dk; e[k] = beta; taus[k] = tau; }
             __syncthreads();
             const int jb = (k + 1) & ~3;
             float yi = 0.f;
             if (active) {
-                const float *ar = A + i * LD;
+                const float *ar = A + i * LDq;
                 float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
                 int j = jb;
-                for (; j + 4 < LD; j += 8) {
+                for (; j + 4 < LDq; j += 8) {
                     const float4 a4 = *reinterpret_cast<const float4 *>(ar + j);
                     const float4 b4 = *reinterpret_cast<const float4 *>(ar + j + 4);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j);
@@ -374,7 +457,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                     y0 = fmaf(a4.x, v4.x, y0); y1 = fmaf(a4.y, v4.y, y1); y2 = fmaf(a4.z, v4.z, y2); y3 = fmaf(a4.w, v4.w, y3);
                     y0 = fmaf(b4.x, u4.x, y0); y1 = fmaf(b4.y, u4.y, y1); y2 = fmaf(b4.z, u4.z, y2); y3 = fmaf(b4.w, u4.w, y3);
                 }
-                if (j < LD) {
+                if (j < LDq) {
                     const float4 a4 = *reinterpret_cast<const float4 *>(ar + j);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j);
                     y0 = fmaf(a4.x, v4.x, y0); y1 = fmaf(a4.y, v4.y, y1); y2 = fmaf(a4.z, v4.z, y2); y3 = fmaf(a4.w, v4.w, y3);
@@ -387,10 +470,10 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
             if (active) w[i] = wi;
             __syncthreads();
             if (active) {
-                float *ar = A + i * LD;
+                float *ar = A + i * LDq;
                 const float nvi = -vi, nwi = -wi;
                 int j = jb;
-                for (; j + 4 < LD; j += 8) {
+                for (; j + 4 < LDq; j += 8) {
                     float4 a4 = *reinterpret_cast<float4 *>(ar + j);
                     float4 b4 = *reinterpret_cast<float4 *>(ar + j + 4);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j), w4 = *reinterpret_cast<const float4 *>(w + j);
@@ -402,7 +485,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                     *reinterpret_cast<float4 *>(ar + j) = a4;
                     *reinterpret_cast<float4 *>(ar + j + 4) = b4;
                 }
-                if (j < LD) {
+                if (j < LDq) {
                     float4 a4 = *reinterpret_cast<float4 *>(ar + j);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j), w4 = *reinterpret_cast<const float4 *>(w + j);
                     a4.x = fmaf(nvi, w4.x, fmaf(nwi, v4.x, a4.x)); a4.y = fmaf(nvi, w4.y, fmaf(nwi, v4.y, a4.y));
@@ -413,19 +496,19 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
             __syncthreads();
         }
         if (tid == 0) {
-            d[p - 2] = A[(p - 2) * LD + p - 2];
-            e[p - 2] = A[(p - 2) * LD + p - 1];
-            taus[p - 2] = 0.f;
-            d[p - 1] = A[(p - 1) * LD + p - 1];
-            e[p - 1] = 0.f;
+            d[qd - 2] = A[(qd - 2) * LDq + qd - 2];
+            e[qd - 2] = A[(qd - 2) * LDq + qd - 1];
+            taus[qd - 2] = 0.f;
+            d[qd - 1] = A[(qd - 1) * LDq + qd - 1];
+            e[qd - 1] = 0.f;
         }
         __syncthreads();
 
         // -------------------------------------------------------------- 2. eigenvalues above the threshold
         // e2[i] = e[i-1]^2 is the coupling that enters pivot i of the Sturm sequence
         float gl = -3.4e38f, em = 0.f;
-        for (int j = tid; j < p; j += TT) {
-            const float el = j > 0 ? e[j - 1] : 0.f, er = j < p - 1 ? e[j] : 0.f;
+        for (int j = tid; j < qd; j += TT) {
+            const float el = j > 0 ? e[j - 1] : 0.f, er = j < qd - 1 ? e[j] : 0.f;
             e2[j] = el * el;
             gl = fmaxf(gl, d[j] + fabsf(el) + fabsf(er));
             em = fmaxf(em, el * el);
@@ -440,13 +523,13 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
         {       // one Sturm count at the threshold: #eigenvalues < tau_eff
             float q = 1.f;
             int cnt = 0;
-            for (int j = 0; j < p; ++j) {
+            for (int j = 0; j < qd; ++j) {
                 float t = (d[j] - tau_eff) - __fdividef(e2[j], q);
                 if (fabsf(t) < pivmin) t = -pivmin;
                 q = t;
                 cnt += t < 0.f;
             }
-            m = min(p - cnt, P.rank);
+            m = min(qd - cnt, P.rank);
             if (gmax <= tau_eff) m = 0;
         }
         float *Z = R + L.oZ;
@@ -471,7 +554,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                     q[c] = 1.f;
                     cnt[c] = 0;
                 }
-                for (int j = 0; j < p; ++j) {             // 4 interleaved Sturm chains: #eigenvalues < x[c]
+                for (int j = 0; j < qd; ++j) {             // 4 interleaved Sturm chains: #eigenvalues < x[c]
                     const float dj = d[j], e2j = e2[j];
 #pragma unroll
                     for (int c = 0; c < ILP; ++c) {
@@ -484,7 +567,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
 #pragma unroll
                 for (int c = 0; c < ILP; ++c)
                     if (ej[c] >= 0) {
-                        const int idx = p - 1 - ej[c];   // ascending index of the ej-th largest eigenvalue
+                        const int idx = qd - 1 - ej[c];   // ascending index of the ej-th largest eigenvalue
                         if (cnt[c] <= idx) atomicMax(&nlo[ej[c]], __float_as_int(x[c]));   // x is a lower bound
                         else atomicMin(&nhi[ej[c]], __float_as_int(x[c]));                  // x is an upper bound
                     }
@@ -506,31 +589,31 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
 
             // ---------------------------------------------------------- 3. eigenvectors of T (twisted factorisation)
             if (tid < m) {
-                float *z = Z + tid * ZS;
+                float *z = Z + tid * ZSq;
                 const float l = lam[tid];
                 const float pm = fmaxf(pivmin, 1e-10f * fabsf(l));
                 float dp = d[0] - l;                       // forward pivots D+ (kept in z)
                 if (fabsf(dp) < pm) dp = -pm;
                 z[0] = dp;
-                for (int i = 0; i < p - 1; ++i) {
+                for (int i = 0; i < qd - 1; ++i) {
                     dp = (d[i + 1] - l) - e2[i + 1] / dp;
                     if (fabsf(dp) < pm) dp = -pm;
                     z[i + 1] = dp;
                 }
-                float dm = d[p - 1] - l;                   // backward pivots D-: twist index r = argmin |gamma_i|
+                float dm = d[qd - 1] - l;                   // backward pivots D-: twist index r = argmin |gamma_i|
                 if (fabsf(dm) < pm) dm = -pm;
-                float best = fabsf(z[p - 1]);
-                int r = p - 1;
-                for (int i = p - 2; i >= 0; --i) {
+                float best = fabsf(z[qd - 1]);
+                int r = qd - 1;
+                for (int i = qd - 2; i >= 0; --i) {
                     dm = (d[i] - l) - e2[i + 1] / dm;
                     if (fabsf(dm) < pm) dm = -pm;
                     const float gam = fabsf(z[i] + dm - (d[i] - l));
                     if (gam < best) { best = gam; r = i; }
                 }
-                dm = d[p - 1] - l;                         // second pass stores D-_i for i > r
+                dm = d[qd - 1] - l;                         // second pass stores D-_i for i > r
                 if (fabsf(dm) < pm) dm = -pm;
-                if (r < p - 1) z[p - 1] = dm;
-                for (int i = p - 2; i > r; --i) {
+                if (r < qd - 1) z[qd - 1] = dm;
+                for (int i = qd - 2; i > r; --i) {
                     dm = (d[i] - l) - e2[i + 1] / dm;
                     if (fabsf(dm) < pm) dm = -pm;
                     z[i] = dm;
@@ -542,57 +625,77 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                     nrm = fmaf(zi, zi, nrm);
                 }
                 zi = 1.f;
-                for (int i = r; i < p - 1; ++i) {
+                for (int i = r; i < qd - 1; ++i) {
                     zi = -(e[i] / z[i + 1]) * zi;
                     z[i + 1] = zi;
                     nrm = fmaf(zi, zi, nrm);
                 }
                 z[r] = 1.f;
                 const float sc = rsqrtf(nrm);
-                for (int i = 0; i < p; ++i) z[i] *= sc;
+                for (int i = 0; i < qd; ++i) z[i] *= sc;
             }
             __syncthreads();
 
-            // ---------------------------------------------------------- 4. back-transformation  z <- H_0 ... H_{p-3} z
+            // ---------------------------------------------------------- 4. back-transformation  z <- H_0 ... H_{qd-3} z
             {
                 int S = 2;                                   // lanes per eigenvector (power of two, S*m <= 128)
                 while (S * 2 * m <= TT && S < 32) S *= 2;
                 const int vec = tid / S, part = tid - vec * S;
                 const bool on = vec < m;
-                float *z = Z + min(vec, m - 1) * ZS;
-                for (int k = p - 3; k >= 0; --k) {
+                float *z = Z + min(vec, m - 1) * ZSq;
+                for (int k = qd - 3; k >= 0; --k) {
                     const float tau = taus[k];
                     if (tau == 0.f) continue;
-                    const float *vr = R + (k * (p - 1) - (k * (k - 1)) / 2) - (k + 1);   // vr[i], i = k+1..p-1
+                    const float *vr = R + (k * (qd - 1) - (k * (k - 1)) / 2) - (k + 1);   // vr[i], i = k+1..qd-1
                     float s0 = 0.f, s1 = 0.f;
                     int i = k + 1 + part;
-                    for (; i + S < p; i += 2 * S) { s0 = fmaf(vr[i], z[i], s0); s1 = fmaf(vr[i + S], z[i + S], s1); }
-                    if (i < p) s0 = fmaf(vr[i], z[i], s0);
+                    for (; i + S < qd; i += 2 * S) { s0 = fmaf(vr[i], z[i], s0); s1 = fmaf(vr[i + S], z[i + S], s1); }
+                    if (i < qd) s0 = fmaf(vr[i], z[i], s0);
                     float s = s0 + s1;
                     for (int dlt = S >> 1; dlt > 0; dlt >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dlt);
                     s *= tau;
                     if (on)
-                        for (int ii = k + 1 + part; ii < p; ii += S) z[ii] = fmaf(-s, vr[ii], z[ii]);
+                        for (int ii = k + 1 + part; ii < qd; ii += S) z[ii] = fmaf(-s, vr[ii], z[ii]);
                     __syncwarp();
                 }
             }
             __syncthreads();
-            // eigenvectors re-laid as Vt[j][r] at the head of R (r contiguous, pitch MR): 4 eigenpairs per broadcast LDS.128
-            for (int idx = tid; idx < p * (MR / 4); idx += TT)
-                reinterpret_cast<float4 *>(R)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
-            for (int r = warp; r < m; r += TT / 32)
+            if (!L.gram) {
+                // eigenvectors re-laid as Vt[j][r] (r contiguous, pitch MR): 4 eigenpairs per broadcast LDS.128
+                float *Vt = R + L.oVt;
+                for (int idx = tid; idx < p * (MR / 4); idx += TT)
+                    reinterpret_cast<float4 *>(Vt)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncthreads();
+                for (int r = warp; r < m; r += TT / 32)
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int j = lane + 32 * qq;
-                    if (j < p) R[j * MR + r] = Z[r * ZS + j];
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int j = lane + 32 * qq;
+                        if (j < p) Vt[j * MR + r] = Z[r * ZSq + j];
+                    }
+            } else {
+                // Gram trick: Ut[nn][r] at the head of R, then v_r = Y^T u_r / sqrt(n lambda_r) straight into Vt[j][r]
+                float *Ut = R;
+                for (int idx = tid; idx < n * (MR / 4); idx += TT)
+                    reinterpret_cast<float4 *>(Ut)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncthreads();
+                for (int r = warp; r < m; r += TT / 32)
+                    for (int nn = lane; nn < n; nn += 32) Ut[nn * MR + r] = Z[r * ZSq + nn];
+                __syncthreads();                          // Z is dead from here on: Vt may overlap it
+                float *Vt = R + L.oVt;
+                switch ((m + 7) >> 3) {
+                    case 1: gram_map<1>(Vt, Ut, lam, mean, src, pb, FUSED, rstride, n, p, m, tid < p ? col_off(tid, ch) : 0, tid); break;
+                    case 2: gram_map<2>(Vt, Ut, lam, mean, src, pb, FUSED, rstride, n, p, m, tid < p ? col_off(tid, ch) : 0, tid); break;
+                    case 3: gram_map<3>(Vt, Ut, lam, mean, src, pb, FUSED, rstride, n, p, m, tid < p ? col_off(tid, ch) : 0, tid); break;
+                    case 4: gram_map<4>(Vt, Ut, lam, mean, src, pb, FUSED, rstride, n, p, m, tid < p ? col_off(tid, ch) : 0, tid); break;
+                    default: gram_map<5>(Vt, Ut, lam, mean, src, pb, FUSED, rstride, n, p, m, tid < p ? col_off(tid, ch) : 0, tid); break;
                 }
+            }
         }
         __syncthreads();
 
         // -------------------------------------------------------------- 5. Wiener filter of the noisy patches
         float *X = R + L.oX;                             // X[xrows][XS], XS odd => conflict-free rows
-        const float *Vt = R;
+        const float *Vt = R + L.oVt;
         if (P.cov_from_basic || FUSED) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) co[q] = col_off(min(lane + 32 * q, p - 1), ch);
@@ -673,7 +776,7 @@ bool bayes_tridiag_supported(const VnlbBayesParams *p) {
     const int pd = p->pt * p->ps * p->ps;
     if (pd < 3 || pd > TT || p->rank > MR || p->k < 1) return false;
     const TriLayout L = tri_layout(p->k, pd);
-    return (size_t)L.total * sizeof(float) <= 227 * 1024 && ((L.LD >> 2) * ((L.LD >> 2) + 1) / 2) <= 3 * TT;
+    return (size_t)L.total * sizeof(float) <= 227 * 1024 && ((L.LDq >> 2) * ((L.LDq >> 2) + 1) / 2) <= 3 * TT;
 }
 
 int launch_bayes_tridiag(float *pnoisy, const float *pbasic, const unsigned char *flat, const long long *inds, int B,
