@@ -37,6 +37,10 @@ struct alignas(16) SearchShared {
     unsigned int sel_neq;
     int sel_last;
     int sel_count;
+    unsigned int red_min[8];
+    unsigned int red_max[8];
+    int sel_bin;
+    unsigned int sel_less;
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -124,99 +128,22 @@ __device__ __forceinline__ void cand_coords(const SearchShared &S, int cand, int
 }
 
 // ---------------------------------------------------------------------------
-// selection: the m = min(k, ncand) smallest (dist, order) pairs, sorted.
-// dist[] (shared) holds the distance of every candidate in enumeration order.
-// keys[] (shared, P = pow2 >= m entries of 64 bit) is scratch.
+// selection: the m = min(k, ncand) smallest (dist, order) pairs, sorted ascending.
+// dist[] (shared) holds the distance of every candidate in enumeration order;
+// keys[] (shared, kKeyCap 64-bit entries) is scratch; tmin/tmax are this
+// thread's smallest/largest distance bits (any subset; reduced here).
+//
+// Fast path: one histogram over 256 bins spread across the ACTUAL range of the
+// distance bits (little atomic contention) finds the bin holding the m-th
+// smallest; everything up to and including that bin (usually 100-300 keys) is
+// bitonic-sorted on (distance bits, enumeration order).  If that set exceeds
+// kKeyCap (heavy ties, e.g. a constant image) the exact 4-pass radix select
+// with ballot-scan tie resolution takes over.  Both give the same answer.
 // ---------------------------------------------------------------------------
-__device__ void select_topk(SearchShared &S, const float *dist, unsigned long long *keys, int P, int k,
-                            float *__restrict__ out_vals, long long *__restrict__ out_inds, int C, int H,
-                            int W) {
+constexpr int kKeyCap = 512;
+
+__device__ void bitonic_sort_keys(unsigned long long *keys, int P) {
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int ncand = S.ncand;
-    const int m = min(k, ncand);
-    if (m > 0) {
-        if (tid == 0) {
-            S.sel_prefix = 0u;
-            S.sel_kk = (unsigned)m;
-            S.sel_count = 0;
-        }
-        unsigned int known = 0u;
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            for (int i = tid; i < 256; i += nthr) S.hist[i] = 0u;
-            __syncthreads();
-            const unsigned int prefix = S.sel_prefix;
-            for (int i = tid; i < ncand; i += nthr) {
-                const unsigned int u = __float_as_uint(dist[i]);
-                if ((u & known) == prefix) atomicAdd(&S.hist[(u >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (tid < 32) {  // warp 0 finds the bin holding the kk-th element
-                unsigned int loc[8], s = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    loc[j] = S.hist[tid * 8 + j];
-                    s += loc[j];
-                }
-                unsigned int incl = s;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (tid >= d) incl += v;
-                }
-                const unsigned int excl = incl - s;
-                const unsigned int kk = S.sel_kk;
-                __syncwarp();
-                if (kk > excl && kk <= incl) {  // exactly one lane
-                    unsigned int run = excl;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (kk > run && kk <= run + loc[j]) {
-                            S.sel_prefix = prefix | ((unsigned)(tid * 8 + j) << shift);
-                            S.sel_kk = kk - run;
-                            S.sel_neq = loc[j];
-                        }
-                        run += loc[j];
-                    }
-                }
-            }
-            known |= 255u << shift;
-            __syncthreads();
-        }
-        const unsigned int vk = S.sel_prefix;  // bits of the m-th smallest distance
-        // among the sel_neq candidates equal to vk keep the sel_kk first in enumeration order
-        if (tid < 32) {
-            int last = ncand - 1;
-            if (S.sel_neq > S.sel_kk) {
-                unsigned int need = S.sel_kk;
-                for (int base = 0; base < ncand; base += 32) {
-                    const int i = base + tid;
-                    const bool eq = i < ncand && __float_as_uint(dist[i]) == vk;
-                    const unsigned int b = __ballot_sync(0xffffffffu, eq);
-                    const unsigned int cnt = __popc(b);
-                    if (cnt >= need) {  // the need-th set bit of b
-                        unsigned int bb = b;
-                        for (unsigned int j = 1; j < need; ++j) bb &= bb - 1;
-                        last = base + __ffs(bb) - 1;
-                        break;
-                    }
-                    need -= cnt;
-                }
-            }
-            if (tid == 0) S.sel_last = last;
-        }
-        __syncthreads();
-        const int last = S.sel_last;
-        for (int i = tid; i < ncand; i += nthr) {
-            const unsigned int u = __float_as_uint(dist[i]);
-            if (u < vk || (u == vk && i <= last)) {
-                const int slot = atomicAdd(&S.sel_count, 1);
-                keys[slot] = ((unsigned long long)u << 32) | (unsigned)i;
-            }
-        }
-    }
-    for (int i = m + tid; i < P; i += nthr) keys[i] = ~0ull;
-    __syncthreads();
-    // bitonic sort of P keys
     for (int size = 2; size <= P; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = tid; i < P / 2; i += nthr) {
@@ -231,6 +158,147 @@ __device__ void select_topk(SearchShared &S, const float *dist, unsigned long lo
             }
             __syncthreads();
         }
+}
+
+__device__ void select_topk(SearchShared &S, const float *dist, unsigned long long *keys, int k, unsigned int tmin,
+                            unsigned int tmax, float *__restrict__ out_vals, long long *__restrict__ out_inds, int C,
+                            int H, int W) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int ncand = S.ncand;
+    const int m = min(k, ncand);
+    int P = 1;
+    while (P < m) P <<= 1;
+    if (m > 0) {
+        // ---- range of the distance bits ----
+        for (int d = 16; d > 0; d >>= 1) {
+            tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, d));
+            tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, d));
+        }
+        if ((tid & 31) == 0) { S.red_min[tid >> 5] = tmin; S.red_max[tid >> 5] = tmax; }
+        for (int i = tid; i < 256; i += nthr) S.hist[i] = 0u;
+        if (tid == 0) S.sel_count = 0;
+        __syncthreads();
+        unsigned int umin = 0xffffffffu, umax = 0u;
+        for (int wv = 0; wv < (nthr + 31) / 32; ++wv) { umin = min(umin, S.red_min[wv]); umax = max(umax, S.red_max[wv]); }
+        const unsigned int range = umax - umin;
+        const int sh = range ? max(0, (32 - __clz(range)) - 8) : 0;
+        for (int i = tid; i < ncand; i += nthr)
+            atomicAdd(&S.hist[(__float_as_uint(dist[i]) - umin) >> sh], 1u);
+        __syncthreads();
+        if (tid < 32) {  // warp 0: bin holding the m-th smallest
+            unsigned int loc[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = S.hist[tid * 8 + j]; s += loc[j]; }
+            unsigned int incl = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += v;
+            }
+            const unsigned int excl = incl - s;
+            if ((unsigned)m > excl && (unsigned)m <= incl) {
+                unsigned int run = excl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if ((unsigned)m > run && (unsigned)m <= run + loc[j]) { S.sel_bin = tid * 8 + j; S.sel_less = run + loc[j]; }
+                    run += loc[j];
+                }
+            }
+        }
+        __syncthreads();
+        const int bin = S.sel_bin;
+        const int total = (int)S.sel_less;           // candidates in bins <= bin (>= m)
+        if (total <= kKeyCap) {
+            for (int i = tid; i < ncand; i += nthr) {
+                const unsigned int u = __float_as_uint(dist[i]);
+                if ((int)((u - umin) >> sh) <= bin) {
+                    const int slot = atomicAdd(&S.sel_count, 1);
+                    keys[slot] = ((unsigned long long)u << 32) | (unsigned)i;
+                }
+            }
+            P = 1;
+            while (P < total) P <<= 1;
+            for (int i = total + tid; i < P; i += nthr) keys[i] = ~0ull;
+            __syncthreads();
+        } else {
+            // ---- exact 4-pass radix select on the distance bits ----
+            if (tid == 0) { S.sel_prefix = 0u; S.sel_kk = (unsigned)m; }
+            unsigned int known = 0u;
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                __syncthreads();
+                for (int i = tid; i < 256; i += nthr) S.hist[i] = 0u;
+                __syncthreads();
+                const unsigned int prefix = S.sel_prefix;
+                for (int i = tid; i < ncand; i += nthr) {
+                    const unsigned int u = __float_as_uint(dist[i]);
+                    if ((u & known) == prefix) atomicAdd(&S.hist[(u >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (tid < 32) {
+                    unsigned int loc[8], s = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { loc[j] = S.hist[tid * 8 + j]; s += loc[j]; }
+                    unsigned int incl = s;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (tid >= d) incl += v;
+                    }
+                    const unsigned int excl = incl - s;
+                    const unsigned int kk = S.sel_kk;
+                    __syncwarp();
+                    if (kk > excl && kk <= incl) {  // exactly one lane
+                        unsigned int run = excl;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (kk > run && kk <= run + loc[j]) {
+                                S.sel_prefix = prefix | ((unsigned)(tid * 8 + j) << shift);
+                                S.sel_kk = kk - run;
+                                S.sel_neq = loc[j];
+                            }
+                            run += loc[j];
+                        }
+                    }
+                }
+                known |= 255u << shift;
+            }
+            __syncthreads();
+            const unsigned int vk = S.sel_prefix;  // bits of the m-th smallest distance
+            // among the sel_neq candidates equal to vk keep the sel_kk first in enumeration order
+            if (tid < 32) {
+                int last = ncand - 1;
+                if (S.sel_neq > S.sel_kk) {
+                    unsigned int need = S.sel_kk;
+                    for (int base = 0; base < ncand; base += 32) {
+                        const int i = base + tid;
+                        const bool eq = i < ncand && __float_as_uint(dist[i]) == vk;
+                        const unsigned int bb = __ballot_sync(0xffffffffu, eq);
+                        const unsigned int cnt = __popc(bb);
+                        if (cnt >= need) {  // the need-th set bit of bb
+                            unsigned int b2 = bb;
+                            for (unsigned int j = 1; j < need; ++j) b2 &= b2 - 1;
+                            last = base + __ffs(b2) - 1;
+                            break;
+                        }
+                        need -= cnt;
+                    }
+                }
+                if (tid == 0) S.sel_last = last;
+            }
+            __syncthreads();
+            const int last = S.sel_last;
+            for (int i = tid; i < ncand; i += nthr) {
+                const unsigned int u = __float_as_uint(dist[i]);
+                if (u < vk || (u == vk && i <= last)) {
+                    const int slot = atomicAdd(&S.sel_count, 1);
+                    keys[slot] = ((unsigned long long)u << 32) | (unsigned)i;
+                }
+            }
+            for (int i = m + tid; i < P; i += nthr) keys[i] = ~0ull;
+            __syncthreads();
+        }
+        bitonic_sort_keys(keys, P);
+    }
     const long long CHW = (long long)C * H * W;
     for (int r = tid; r < k; r += nthr) {
         if (r < m) {
@@ -259,6 +327,7 @@ search_generic_kernel(const float *__restrict__ img, int T, int C, int H, int W,
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(SearchShared));
     float *dist = reinterpret_cast<float *>(keys + P);
     float *qpatch = dist + ncand_max;
+    unsigned int tmin = 0xffffffffu, tmax = 0u;
 
     const int q = blockIdx.x;
     const int t0 = (int)qinds[3 * q], y0 = (int)qinds[3 * q + 1], x0 = (int)qinds[3 * q + 2];
@@ -300,9 +369,11 @@ search_generic_kernel(const float *__restrict__ img, int T, int C, int H, int W,
                 }
             }
         dist[cand] = d2;
+        tmin = min(tmin, __float_as_uint(d2));
+        tmax = max(tmax, __float_as_uint(d2));
     }
     __syncthreads();
-    select_topk(S, dist, keys, P, p.k, ov, oi, C, H, W);
+    select_topk(S, dist, keys, p.k, tmin, tmax, ov, oi, C, H, W);
 }
 
 // ---------------------------------------------------------------------------
@@ -342,6 +413,7 @@ search_tiled_kernel(const float *__restrict__ img, int T, int C, int H, int W,
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(SearchShared));
     float *dist = reinterpret_cast<float *>(keys + P);
     float *qpatch = dist + ncand_max;                    // [TPT][49] of the current channel (+pad)
+    unsigned int tmin = 0xffffffffu, tmax = 0u;
     float *tiles = qpatch + 2 * 52;                      // [TPT][TCHUNK][TSLOT]
 
     const int q = blockIdx.x;
@@ -379,17 +451,19 @@ search_tiled_kernel(const float *__restrict__ img, int T, int C, int H, int W,
                 const int ht = i / 49, r = i - ht * 49, hy = r / 7, hx = r - hy * 7;
                 qpatch[ht * 52 + r] = img[(long long)(t0 + ht) * CHW + c * HW + (long long)(y0 + hy) * W + x0 + hx];
             }
-            // stage the tiles: slot (fl, ht) <- frame fw[f0+fl].t + ht, window origin of fw[f0+fl]
-            for (int fl = 0; fl < nf; ++fl) {
+            // stage the tiles: slot (ht, fl) <- frame fw[f0+fl].t + ht at the window origin of fw[f0+fl];
+            // one warp per tile row, one lane per column (no integer division)
+            for (int task = (tid >> 5); task < nf * TPT * TTILE; task += kSearchThreads / 32) {
+                const int slot = task / TTILE, r = task - slot * TTILE;   // constant divisor
+                const int fl = slot >> 1, ht = slot & 1;
                 const FrameWin w = S.fw[f0 + fl];
                 const int rows = w.ny + TPS - 1, cols = w.nx + TPS - 1;
-                for (int ht = 0; ht < TPT; ++ht) {
-                    const float *src = img + (long long)(w.t + ht) * CHW + c * HW + (long long)w.y0 * W + w.x0;
-                    float *dst = tiles + (ht * TCHUNK + fl) * TSLOT;
-                    for (int i = tid; i < rows * cols; i += blockDim.x) {
-                        const int r = i / cols, cc = i - r * cols;
-                        cp_async4(dst + r * TPITCH + cc, src + (long long)r * W + cc);
-                    }
+                if (r < rows) {
+                    const float *src = img + (long long)(w.t + ht) * CHW + c * HW + (long long)(w.y0 + r) * W + w.x0;
+                    float *dst = tiles + (ht * TCHUNK + fl) * TSLOT + r * TPITCH;
+                    const int lane = tid & 31;
+                    if (lane < cols) cp_async4(dst + lane, src + lane);
+                    if (lane == 0 && cols > 32) cp_async4(dst + 32, src + 32);
                 }
             }
             cp_async_wait_all();
@@ -430,13 +504,17 @@ search_tiled_kernel(const float *__restrict__ img, int T, int C, int H, int W,
 #pragma unroll
                 for (int s = 0; s < TSTRIP; ++s) {
                     const int r = it_s * TSTRIP + s;
-                    if (r < w.ny) dist[w.off + r * w.nx + it_x] = acc[s];
+                    if (r < w.ny) {
+                        dist[w.off + r * w.nx + it_x] = acc[s];
+                        tmin = min(tmin, __float_as_uint(acc[s]));
+                        tmax = max(tmax, __float_as_uint(acc[s]));
+                    }
                 }
             }
         }
     }
     __syncthreads();
-    select_topk(S, dist, keys, P, p.k, ov, oi, C, H, W);
+    select_topk(S, dist, keys, p.k, tmin, tmax, ov, oi, C, H, W);
 }
 
 // patches[b,n,dt,ch,dy,dx] = img[t+dt,ch,y+dy,x+dx]   (search.py:91-98)
@@ -498,7 +576,7 @@ extern "C" int vnlb_search_topk(const float *img, int T, int C, int H, int W, co
     if (Q == 0) return VNLB_OK;
     const int nfr = p->nWt_f + p->nWt_b + 1;
     const int ncand_max = nfr * p->w_s * p->w_s;
-    const int P = next_pow2(p->k);
+    const int P = next_pow2(p->k) > kKeyCap ? next_pow2(p->k) : kKeyCap;   // 64-bit key slots in shared memory
     const bool tiled = tiled_ok(p);
     size_t smem = sizeof(SearchShared) + (size_t)P * 8 + (size_t)ncand_max * 4;
     if (tiled)

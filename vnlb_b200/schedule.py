@@ -21,7 +21,7 @@ from .flat_areas import update_flat_patch
 from .proc_nl import finish_step
 from .utils import AttrDict
 
-FAST_DEFAULTS = dict(fast_frac=1. / 32, fast_min=2048, fast_cap=16384, fast_seed=123)
+FAST_DEFAULTS = dict(fast_frac=1. / 8, fast_min=4096, fast_cap=16384, fast_seed=123)
 
 
 class _Workspace:
