@@ -169,60 +169,53 @@ __device__ void select_topk(SearchShared &S, const float *dist, unsigned long lo
     int P = 1;
     while (P < m) P <<= 1;
     if (m > 0) {
-        // ---- range of the distance bits ----
-        for (int d = 16; d > 0; d >>= 1) {
-            tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, d));
-            tmax = max(tmax, __shfl_xor_sync(0xffffffffu, tmax, d));
-        }
-        if ((tid & 31) == 0) { S.red_min[tid >> 5] = tmin; S.red_max[tid >> 5] = tmax; }
-        for (int i = tid; i < 256; i += nthr) S.hist[i] = 0u;
+        // ---- fast path: pivot from a sorted sample of kKeyCap candidates ----
         if (tid == 0) S.sel_count = 0;
-        __syncthreads();
-        unsigned int umin = 0xffffffffu, umax = 0u;
-        for (int wv = 0; wv < (nthr + 31) / 32; ++wv) { umin = min(umin, S.red_min[wv]); umax = max(umax, S.red_max[wv]); }
-        const unsigned int range = umax - umin;
-        const int sh = range ? max(0, (32 - __clz(range)) - 8) : 0;
-        for (int i = tid; i < ncand; i += nthr)
-            atomicAdd(&S.hist[(__float_as_uint(dist[i]) - umin) >> sh], 1u);
-        __syncthreads();
-        if (tid < 32) {  // warp 0: bin holding the m-th smallest
-            unsigned int loc[8], s = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { loc[j] = S.hist[tid * 8 + j]; s += loc[j]; }
-            unsigned int incl = s;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (tid >= d) incl += v;
-            }
-            const unsigned int excl = incl - s;
-            if ((unsigned)m > excl && (unsigned)m <= incl) {
-                unsigned int run = excl;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if ((unsigned)m > run && (unsigned)m <= run + loc[j]) { S.sel_bin = tid * 8 + j; S.sel_less = run + loc[j]; }
-                    run += loc[j];
-                }
-            }
-        }
-        __syncthreads();
-        const int bin = S.sel_bin;
-        const int total = (int)S.sel_less;           // candidates in bins <= bin (>= m)
-        if (total <= kKeyCap) {
-            for (int i = tid; i < ncand; i += nthr) {
-                const unsigned int u = __float_as_uint(dist[i]);
-                if ((int)((u - umin) >> sh) <= bin) {
-                    const int slot = atomicAdd(&S.sel_count, 1);
-                    keys[slot] = ((unsigned long long)u << 32) | (unsigned)i;
-                }
-            }
+        bool fast = false;
+        unsigned long long pivot = ~0ull;
+        if (ncand <= kKeyCap) {                  // few candidates: sort them all
+            for (int i = tid; i < ncand; i += nthr) keys[i] = ((unsigned long long)__float_as_uint(dist[i]) << 32) | (unsigned)i;
             P = 1;
-            while (P < total) P <<= 1;
-            for (int i = total + tid; i < P; i += nthr) keys[i] = ~0ull;
+            while (P < ncand) P <<= 1;
+            for (int i = ncand + tid; i < P; i += nthr) keys[i] = ~0ull;
             __syncthreads();
+            fast = true;
+        } else {
+            for (int j = tid; j < kKeyCap; j += nthr) {
+                const int i = (int)(((long long)j * ncand) / kKeyCap);
+                keys[j] = ((unsigned long long)__float_as_uint(dist[i]) << 32) | (unsigned)i;
+            }
+            __syncthreads();
+            bitonic_sort_keys(keys, kKeyCap);
+            // expected #candidates <= pivot: ncand*(rk+1)/kKeyCap ~ 2 m + margin, relative spread ~ 1/sqrt(rk)
+            const int rk = min(kKeyCap - 1, (int)((2.0f * (float)m * (float)kKeyCap) / (float)ncand) + 6);
+            pivot = keys[rk];
+            __syncthreads();
+            for (int i = tid; i < ncand; i += nthr) {
+                const unsigned long long key = ((unsigned long long)__float_as_uint(dist[i]) << 32) | (unsigned)i;
+                if (key <= pivot) {
+                    const int slot = atomicAdd(&S.sel_count, 1);
+                    if (slot < kKeyCap) keys[slot] = key;
+                }
+            }
+            __syncthreads();
+            const int total = S.sel_count;
+            if (total >= m && total <= kKeyCap) {
+                P = 1;
+                while (P < total) P <<= 1;
+                for (int i = total + tid; i < P; i += nthr) keys[i] = ~0ull;
+                fast = true;
+            }
+            __syncthreads();
+        }
+        (void)tmin; (void)tmax;
+        if (fast) {
+            // keys[0..P) hold a superset of the m smallest; sorted below
         } else {
             // ---- exact 4-pass radix select on the distance bits ----
-            if (tid == 0) { S.sel_prefix = 0u; S.sel_kk = (unsigned)m; }
+            if (tid == 0) { S.sel_prefix = 0u; S.sel_kk = (unsigned)m; S.sel_count = 0; }
+            P = 1;
+            while (P < m) P <<= 1;
             unsigned int known = 0u;
             for (int shift = 24; shift >= 0; shift -= 8) {
                 __syncthreads();
@@ -444,6 +437,14 @@ search_tiled_kernel(const float *__restrict__ img, int T, int C, int H, int W,
 #pragma unroll
         for (int s = 0; s < TSTRIP; ++s) acc[s] = 0.f;
         const bool active = has_item && it_f < nf;
+        bool shared_win = true;   // all frames of the chunk share one window and are consecutive
+        {
+            const FrameWin w0 = S.fw[f0];
+            for (int fl = 1; fl < nf; ++fl) {
+                const FrameWin w = S.fw[f0 + fl];
+                shared_win = shared_win && w.x0 == w0.x0 && w.y0 == w0.y0 && w.nx == w0.nx && w.ny == w0.ny && w.t == w0.t + fl;
+            }
+        }
         for (int c = 0; c < dc; ++c) {
             __syncthreads();  // previous phase done with tiles / qpatch
             // stage the query planes of channel c
@@ -451,19 +452,25 @@ search_tiled_kernel(const float *__restrict__ img, int T, int C, int H, int W,
                 const int ht = i / 49, r = i - ht * 49, hy = r / 7, hx = r - hy * 7;
                 qpatch[ht * 52 + r] = img[(long long)(t0 + ht) * CHW + c * HW + (long long)(y0 + hy) * W + x0 + hx];
             }
-            // stage the tiles: slot (ht, fl) <- frame fw[f0+fl].t + ht at the window origin of fw[f0+fl];
-            // one warp per tile row, one lane per column (no integer division)
-            for (int task = (tid >> 5); task < nf * TPT * TTILE; task += kSearchThreads / 32) {
-                const int slot = task / TTILE, r = task - slot * TTILE;   // constant divisor
-                const int fl = slot >> 1, ht = slot & 1;
-                const FrameWin w = S.fw[f0 + fl];
-                const int rows = w.ny + TPS - 1, cols = w.nx + TPS - 1;
-                if (r < rows) {
-                    const float *src = img + (long long)(w.t + ht) * CHW + c * HW + (long long)(w.y0 + r) * W + w.x0;
-                    float *dst = tiles + (ht * TCHUNK + fl) * TSLOT + r * TPITCH;
-                    const int lane = tid & 31;
-                    if (lane < cols) cp_async4(dst + lane, src + lane);
-                    if (lane == 0 && cols > 32) cp_async4(dst + 32, src + 32);
+            // stage the tiles.  Zero flow (or a rigid trajectory): every frame of the chunk has the same
+            // window, so slot s <- frame t0c + s and the item (frame fl, plane ht) reads slot fl + ht
+            // (nf + 1 tiles instead of 2 nf).  Otherwise slot (ht, fl) <- frame fw[f0+fl].t + ht at the
+            // window of fw[f0+fl].  One warp per tile row, one lane per column.
+            {
+                const int lane = tid & 31, wrp = tid >> 5;
+                const int nslots = shared_win ? nf + 1 : nf * TPT;
+                for (int sl = 0; sl < nslots; ++sl) {
+                    const int fl = shared_win ? 0 : (sl >> 1), ht = shared_win ? sl : (sl & 1);
+                    const FrameWin w = S.fw[f0 + fl];
+                    const int rows = w.ny + TPS - 1, cols = w.nx + TPS - 1;
+                    const float *src = img + (long long)(w.t + ht) * CHW + c * HW + (long long)(w.y0 + wrp) * W + w.x0;
+                    float *dst = tiles + (shared_win ? sl : (sl & 1) * TCHUNK + fl) * TSLOT + wrp * TPITCH;
+                    for (int r = wrp; r < rows; r += kSearchThreads / 32) {
+                        if (lane < cols) cp_async4(dst + lane, src + lane);
+                        if (lane == 0 && cols > 32) cp_async4(dst + 32, src + 32);
+                        src += (long long)(kSearchThreads / 32) * W;
+                        dst += (kSearchThreads / 32) * TPITCH;
+                    }
                 }
             }
             cp_async_wait_all();
@@ -476,7 +483,7 @@ search_tiled_kernel(const float *__restrict__ img, int T, int C, int H, int W,
                         float qv[49];
 #pragma unroll
                         for (int i = 0; i < 49; ++i) qv[i] = qpatch[ht * 52 + i];
-                        const float *tp = tiles + (ht * TCHUNK + it_f) * TSLOT + (it_s * TSTRIP) * TPITCH + it_x;
+                        const float *tp = tiles + (shared_win ? it_f + ht : ht * TCHUNK + it_f) * TSLOT + (it_s * TSTRIP) * TPITCH + it_x;
 #pragma unroll
                         for (int rho = 0; rho < TSTRIP + TPS - 1; ++rho) {
                             float v[7];
