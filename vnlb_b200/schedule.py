@@ -40,13 +40,77 @@ class _Workspace:
             ws.noisy = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
             ws.basic = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
             ws.flat = torch.zeros((cap,), dtype=torch.uint8, device=device)
-            ws.vals = torch.empty((cap, k), dtype=torch.float32, device=device)
-            ws.inds = torch.empty((cap, k), dtype=torch.int64, device=device)
-            ws.qinds = torch.empty((cap, 3), dtype=torch.int64, device=device)
+            # two sets of round buffers: the search of round r+1 overlaps the Bayes kernel of round r
+            ws.vals2 = [torch.empty((cap, k), dtype=torch.float32, device=device) for _ in range(2)]
+            ws.inds2 = [torch.empty((cap, k), dtype=torch.int64, device=device) for _ in range(2)]
+            ws.qinds2 = [torch.empty((cap, 3), dtype=torch.int64, device=device) for _ in range(2)]
+            ws.vals, ws.inds, ws.qinds = ws.vals2[0], ws.inds2[0], ws.qinds2[0]
+            ws.search_stream = torch.cuda.Stream(device=device)
+            ws.bayes_stream = torch.cuda.Stream(device=device)
             ws.counters = torch.zeros((2,), dtype=torch.int32, device=device)
             ws.host = torch.zeros((2,), dtype=torch.int32).pin_memory()
             cls._cache[key] = ws
         return ws
+
+
+def _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed):
+    """The rounds of one step on two streams: [count, draw, search, clear mask] of round r+1 runs on
+    the search stream while the fused Bayes kernel of round r runs on the Bayes stream (the mask only
+    depends on the search results, never on the filtered patches)."""
+    t, c, h, w = images.shape
+    main = torch.cuda.current_stream()
+    sA, sB = ws.search_stream, ws.bayes_stream
+    sA.wait_stream(main)
+    sB.wait_stream(main)
+    done_search = [None, None]      # event: inds2[b] written and mask updated
+    done_bayes = [None, None]       # event: inds2[b] consumed
+    nproc, nrounds, nmask0, buf = 0, 0, None, 0
+    tm = L.timer
+    while True:
+        with torch.cuda.stream(sA):
+            st = L.stream_ptr()
+            ws.counters.zero_()
+            L.check(L.lib.vnlb_count_mask(L.ptr(mask), t, h, w, L.ptr(ws.counters), st), "vnlb_count_mask")
+            ws.host.copy_(ws.counters, non_blocking=True)
+            sA.synchronize()
+            remaining = int(ws.host[0])
+            if nmask0 is None:
+                nmask0 = remaining
+            if remaining == 0:
+                break
+            target = min(cap, max(qmin, int(remaining * frac)))
+            prob = 1.0 if remaining <= target else target / remaining * 0.97   # stay under cap
+            if done_bayes[buf] is not None:
+                sA.wait_event(done_bayes[buf])                               # round r-2 is done with this buffer
+            qinds, vals, inds = ws.qinds2[buf], ws.vals2[buf], ws.inds2[buf]
+            L.check(L.lib.vnlb_select_queries(L.ptr(mask), t, h, w, prob, seed, nrounds, L.ptr(qinds), cap,
+                                              L.ptr(ws.counters), st), "vnlb_select_queries")
+            ws.host.copy_(ws.counters, non_blocking=True)
+            sA.synchronize()
+            q = min(int(ws.host[1]), cap)
+            nrounds += 1
+            if q == 0:
+                continue
+            tok = tm.start("search") if tm else None
+            search.exec_sim_search_burst(srch_img, qinds[:q], vals[:q], inds[:q], flows, args.sigma, args)
+            if tm:
+                tm.stop(tok)
+            search_mask.update_mask_inds(mask, inds[:q], c, boost=args.aggreBoost)
+            done_search[buf] = torch.cuda.Event()
+            done_search[buf].record(sA)
+        with torch.cuda.stream(sB):
+            sB.wait_event(done_search[buf])
+            tok = tm.start("bayes") if tm else None
+            deno.bayes_aggregate_fused(images, inds[:q], args)
+            if tm:
+                tm.stop(tok)
+            done_bayes[buf] = torch.cuda.Event()
+            done_bayes[buf].record(sB)
+        nproc += q
+        buf ^= 1
+    main.wait_stream(sA)
+    main.wait_stream(sB)
+    return nproc, nrounds, nmask0
 
 
 def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
@@ -70,6 +134,14 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
     if srch_img is None:
         raise ValueError("uknown search image [%s]" % args.srch_img)
     nproc, nrounds, nmask0 = 0, 0, None
+    if fused and bool(args.get("fast_overlap", True)):
+        nproc, nrounds, nmask0 = _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed)
+        finish_step(images, args, reduce_fn)
+        if stats is not None:
+            stats.setdefault("ngroups", []).append(nproc)
+            stats.setdefault("nmask", []).append(nmask0)
+            stats.setdefault("nrounds", []).append(nrounds)
+        return
     while True:
         ws.counters.zero_()
         L.check(L.lib.vnlb_count_mask(L.ptr(mask), t, h, w, L.ptr(ws.counters), st), "vnlb_count_mask")
