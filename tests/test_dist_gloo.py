@@ -31,6 +31,16 @@ def test_partition_rows_covers_every_reference_row_once():
         assert max(sizes) - min(sizes) <= 1 and min(sizes) > 0
 
 
+def test_snake_partition_is_a_partition():
+    from vnlb_b200.dist import partition_rows_snake
+    for h, world in [(480, 2), (3840, 8), (960, 4)]:
+        rows = []
+        for r in range(world):
+            for (a, b) in partition_rows_snake(h, 7, world, r):
+                rows += list(range(a, min(b, h - 6)))
+        assert sorted(rows) == list(range(h - 6))
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

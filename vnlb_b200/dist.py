@@ -30,6 +30,17 @@ def partition_rows(h, ps, world_size, rank):
     return y0, y1
 
 
+def partition_rows_snake(h, ps, world_size, rank):
+    """Two bands per rank, assigned boustrophedon (rank r owns bands r and 2N-1-r of 2N), so that
+    content that changes from the top to the bottom of the frame is averaged over the ranks:
+    the number of groups a band produces depends on its texture, not only on its size."""
+    if world_size == 1:
+        return [partition_rows(h, ps, 1, 0)]
+    a = partition_rows(h, ps, 2 * world_size, rank)
+    b = partition_rows(h, ps, 2 * world_size, 2 * world_size - 1 - rank)
+    return [a, b]
+
+
 def allreduce_accumulators(images, group=None):
     """Sum the aggregation accumulators over ranks (border overlap + band union)."""
     dist.all_reduce(images.deno, op=dist.ReduceOp.SUM, group=group)
@@ -37,7 +48,7 @@ def allreduce_accumulators(images, group=None):
 
 
 def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="default", params=None,
-                        stats=None, group=None, device=None, clean=None):
+                        stats=None, group=None, device=None, clean=None, balance=True):
     """vnlb.denoise over all ranks of `group`.  Every rank passes the same `noisy`
     (host or device) and receives the full (deno, basic, seconds)."""
     clock = Timer()
@@ -62,7 +73,7 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
         for step in (0, 1):
             images = alloc.allocate_images(noisy, basic, clean)
             args = get_args(params, c, step, device)
-            y_range = partition_rows(h, args.ps, world, rank)
+            y_range = partition_rows_snake(h, args.ps, world, rank) if balance else partition_rows(h, args.ps, world, rank)
             if schedule == "fast":
                 step_fn(images, dflows, args, stats, y_range, reduce_fn)
             else:

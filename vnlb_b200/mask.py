@@ -13,11 +13,21 @@ def init_mask(shape, args, device=None, y_range=None):
     restricts the set pixels to a row band (multi-GPU partition)."""
     t, c, h, w = shape
     device = device if device is not None else args.device
-    mask = torch.empty((t, h, w), dtype=torch.int8, device=device)
-    y0, y1 = (0, h) if y_range is None else y_range
-    L.check(L.lib.vnlb_init_mask(L.ptr(mask), t, h, w, args.ps, args.pt, args.procStep, int(y0), int(y1),
-                                 L.stream_ptr()), "vnlb_init_mask")
+    mask = init_mask_device(shape, args, device, y_range)
     return mask, int(mask.sum().item())
+
+
+def init_mask_device(shape, args, device, y_range=None):
+    """The mask only (no host sync).  `y_range`: None, (y0, y1) or a list of such bands."""
+    t, c, h, w = shape
+    bands = [(0, h)] if y_range is None else ([y_range] if isinstance(y_range[0], int) else list(y_range))
+    mask = None
+    for (y0, y1) in bands:
+        m = torch.empty((t, h, w), dtype=torch.int8, device=device)
+        L.check(L.lib.vnlb_init_mask(L.ptr(m), t, h, w, args.ps, args.pt, args.procStep, int(y0), int(y1),
+                                     L.stream_ptr()), "vnlb_init_mask")
+        mask = m if mask is None else torch.bitwise_or(mask, m)
+    return mask
 
 
 def mask2inds(mask, bsize, rand=True, order=None):

@@ -124,11 +124,8 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
     k = args.npatches
     fused = bool(args.get("fused", True)) and deno.fused_supported(args, c)
     ws = _Workspace.get(dev, cap, k, args.pt, c, args.ps, stacks=not fused)
-    mask = torch.empty((t, h, w), dtype=torch.int8, device=dev)
-    y0, y1 = (0, h) if y_range is None else y_range
+    mask = search_mask.init_mask_device(images.shape, args, dev, y_range)
     st = L.stream_ptr()
-    L.check(L.lib.vnlb_init_mask(L.ptr(mask), t, h, w, args.ps, args.pt, args.procStep, int(y0), int(y1), st),
-            "vnlb_init_mask")
     color.rgb2yuv_images(images)
     srch_img = {"noisy": images.noisy, "basic": images.basic, "clean": images.clean}[args.srch_img]
     if srch_img is None:
