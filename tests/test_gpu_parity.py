@@ -428,3 +428,63 @@ def test_e2e_fast_schedule_psnr(vb, golden_dir):
         deno, basic, _ = vb.denoise(noisy, e["sigma"], schedule="fast", verbose=False, params=params)
         ps = [orc.compute_psnrs(a.cpu().numpy(), clean).mean() for a in (basic, deno)]
         assert abs(ps[0] - g["psnrs"][1]) < 0.25 and abs(ps[1] - g["psnrs"][2]) < 0.25, (fused, ps, g["psnrs"])
+
+
+# ---------------------------------------------------------------- end to end: flows and other parameter tables
+def _oracle_params(vb_params):
+    keys = orc.default_params(20.).keys()
+    return {k: list(vb_params[k]) for k in keys}
+
+
+def test_e2e_parity_with_flows(vb):
+    """denoise(flows=...) follows the flow trajectory exactly like the oracle (north-star API)."""
+    T, H, W, sigma = 5, 40, 48, 20.
+    clean = orc.synth_video(T, H, W, 11)
+    noisy = orc.add_noise(clean, sigma, 11)
+    rs = np.random.RandomState(4)
+    flows = dict(fflow=((rs.rand(T - 1, 2, H, W) - 0.5) * 6).astype(np.float32),
+                 bflow=((rs.rand(T - 1, 2, H, W) - 0.5) * 6).astype(np.float32))     # [T-1] -> expanded like the C++ code
+    torch.manual_seed(3)
+    deno, basic, _ = vb.denoise(noisy, sigma, flows=flows, schedule="parity", verbose=False)
+    ff = np.concatenate([flows["fflow"], flows["fflow"][-1:]], 0)
+    bf = np.concatenate([flows["bflow"][:1], flows["bflow"]], 0)
+    torch.manual_seed(3)
+    odeno, obasic, _ = orc.denoise(noisy, sigma, flows=dict(fflow=ff, bflow=bf))
+    assert np.abs(basic.cpu().numpy() - obasic).max() < 1e-2
+    assert np.abs(deno.cpu().numpy() - odeno).max() < 1e-2
+    # and the flows matter: zero-flow output differs
+    torch.manual_seed(3)
+    d0, _, _ = vb.denoise(noisy, sigma, schedule="parity", verbose=False)
+    assert np.abs(d0.cpu().numpy() - odeno).max() > 1e-2
+
+
+def test_e2e_parity_iphone_table(vb):
+    """The reference's shipped parameter overrides (params.py:83-91: pt = [1,2], 15x15 window, +-10
+    frames) with the l2 search: generic search kernel, p = 49 Bayes problems in step 1."""
+    T, H, W, sigma = 4, 36, 40, 20.
+    clean = orc.synth_video(T, H, W, 5)
+    noisy = orc.add_noise(clean, sigma, 5)
+    params = vb.get_params(sigma, version="iphone")
+    stats, ostats = {}, {}
+    torch.manual_seed(9)
+    deno, basic, _ = vb.denoise(noisy, sigma, schedule="parity", verbose=False, params=params, stats=stats)
+    torch.manual_seed(9)
+    odeno, obasic, _ = orc.denoise(noisy, sigma, params=_oracle_params(params), stats=ostats)
+    assert stats["ngroups"] == ostats["ngroups"]
+    assert np.abs(basic.cpu().numpy() - obasic).max() < 1e-2
+    assert np.abs(deno.cpu().numpy() - odeno).max() < 1e-2
+
+
+def test_fast_schedule_is_deterministic_and_serial_equals_overlapped(vb):
+    T, H, W, sigma = 4, 48, 56, 20.
+    noisy = orc.add_noise(orc.synth_video(T, H, W, 2), sigma, 2)
+    outs = []
+    for overlap in (True, True, False):
+        params = vb.get_params(sigma)
+        params["fast_overlap"] = [overlap, overlap]
+        st = {}
+        deno, basic, _ = vb.denoise(noisy, sigma, schedule="fast", verbose=False, params=params, stats=st)
+        outs.append((deno.cpu().numpy(), st["ngroups"]))
+    assert outs[0][1] == outs[1][1] == outs[2][1]                 # same groups drawn (hash-based selection)
+    assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-3           # float-atomic order only
+    assert np.abs(outs[0][0] - outs[2][0]).max() < 1e-3
