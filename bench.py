@@ -217,6 +217,12 @@ def run_ours(args):
     stage = _lib.timer.summary()
     _lib.timer = None
     ngroups = [int(g) for g in st2.get("ngroups", [0, 0])]
+    per_rank = None
+    if world > 1:   # load balance report: groups and device time of the stage pass on every rank
+        mine = torch.tensor([float(sum(ngroups)), float(sum(v["ms"] for v in stage.values()))], device=device)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = dict(groups=[int(a[0].item()) for a in allr], stage_ms=[round(float(a[1].item()), 1) for a in allr])
 
     if rank == 0:
         hbm_peak, peak_kind = load_peaks()
@@ -266,7 +272,7 @@ def run_ours(args):
                      h2d_bytes_per_step=int(noisy.nbytes) * max(world, 1), d2h_bytes_per_step=int(noisy.nbytes)),
             gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
             stages_ms={k: round(v["ms"], 3) for k, v in stage.items()}, groups_per_step=ngroups, psnr=psnr,
-            rounds=st2.get("nrounds"))
+            rounds=st2.get("nrounds"), per_rank=per_rank)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -76,6 +76,7 @@ def _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap,
             remaining = int(ws.host[0])
             if nmask0 is None:
                 nmask0 = remaining
+                qmin = min(qmin, max(296, nmask0 // 64))     # small videos: small rounds keep the greedy mask effective
             if remaining == 0:
                 break
             target = min(cap, max(qmin, int(remaining * frac)))
@@ -147,6 +148,7 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
         remaining = int(ws.host[0])
         if nmask0 is None:
             nmask0 = remaining
+            qmin = min(qmin, max(296, nmask0 // 64))
         if remaining == 0:
             break
         target = min(cap, max(qmin, int(remaining * frac)))
