@@ -52,24 +52,37 @@ static TriLayout tri_layout(int n, int p) {
     L.XS = L.LD + 1;
     // Gram trick: with fewer patches than patch dimensions the non-zero spectrum of
     // C = Y^T Y/n equals that of G = Y Y^T/n and v = Y^T u / sqrt(n lambda); step 2 (n = 60 < p = 98).
-    L.gram = (n + 8 <= p && n >= 3) ? 1 : 0;
+    L.gram = (n + 8 <= p && n >= 3 && n <= 60) ? 1 : 0;   // n <= 60: one 4x4 Gram tile per thread
     L.q = L.gram ? n : p;
     L.LDq = (L.q + 3) & ~3;
     L.ZSq = L.q | 1;
     const int q = L.q;
     const int nref = ((q - 1) * q / 2 + 3) & ~3;            // packed reflectors
-    const int ut = L.gram ? ((n * MR + 3) & ~3) : 0;        // gram: Ut[n][MR] occupies [0, ut)
-    L.oVt = ut;                                             // Vt[p][MR]
-    L.oX = ut + ((p * MR + 3) & ~3);                        // X[xrows][XS]
-    const int head = L.gram ? ut : L.oX;                    // what Z must not overlap while it is transposed
-    L.oZ = nref > head ? nref : head;
-    int rsize = L.LDq * L.LDq;
-    const int chunk = L.gram ? 32 * L.LDq : CH * L.LD;      // staging of phase 0
-    if (rsize < chunk) rsize = chunk;
-    if (rsize < L.oZ + MR * L.ZSq) rsize = L.oZ + MR * L.ZSq;
-    const int want_rows = n < 32 ? n : 32;
-    if (rsize < L.oX + want_rows * L.XS) rsize = L.oX + want_rows * L.XS;
-    if (rsize < L.LD * L.LD && !L.gram) rsize = L.LD * L.LD;
+    int rsize;
+    if (!L.gram) {
+        L.oVt = 0;                                          // Vt[p][MR] at the head of R
+        L.oX = (p * MR + 3) & ~3;                           // X[xrows][XS] behind it
+        L.oZ = nref > L.oX ? nref : L.oX;                   // Z must not overlap the reflectors nor Vt
+        rsize = L.LD * L.LD;
+        if (rsize < CH * L.LD) rsize = CH * L.LD;
+        if (rsize < L.oZ + MR * L.ZSq) rsize = L.oZ + MR * L.ZSq;
+        const int want_rows = n < 32 ? n : 32;
+        if (rsize < L.oX + want_rows * L.XS) rsize = L.oX + want_rows * L.XS;
+    } else {
+        // A (LDq^2), the packed reflectors and the staging chunk live below oZ; Z, then Ut (transposed in
+        // place through registers) at oZ; Vt at the head once the reflectors are dead; X over Ut at the end.
+        L.oVt = 0;
+        L.oZ = (p * MR + 3) & ~3;
+        if (L.oZ < L.LDq * L.LDq) L.oZ = L.LDq * L.LDq;
+        if (L.oZ < 32 * L.LDq) L.oZ = 32 * L.LDq;
+        if (L.oZ < nref) L.oZ = nref;
+        L.oX = L.oZ;
+        int zsz = MR * L.ZSq;
+        if (zsz < n * MR) zsz = n * MR;
+        const int want_rows = n < 32 ? n : 32;
+        if (zsz < want_rows * L.XS) zsz = want_rows * L.XS;
+        rsize = L.oZ + zsz;
+    }
     rsize = (rsize + 3) & ~3;
     L.rsize = rsize;
     L.xrows = (rsize - L.oX) / L.XS;
@@ -232,8 +245,9 @@ __device__ __forceinline__ void gram_map(float *Vt, const float *Ut, const float
     }
 }
 
-template <bool FUSED>
-__global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
+template <bool FUSED, bool GRAM>
+__global__ void __launch_bounds__(TT, GRAM ? 6 : 5) bayes_kernel(const BayesArgs a) {
+    constexpr int NT = GRAM ? 1 : 3;               // 4x4 tiles of the (covariance | Gram) matrix per thread
     extern __shared__ __align__(16) float sm[];
     const VnlbBayesParams &P = a.P;
     const TriLayout &L = a.L;
@@ -324,9 +338,9 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
         for (int j = tid; j < LDq; j += TT) { v[j] = 0.f; w[j] = 0.f; }
         // lower-triangular 4x4 tiles of the qd x qd matrix (covariance or Gram) owned by this thread
         const int ntile = LDq >> 2, ntri = ntile * (ntile + 1) / 2;
-        int ti[3], tj[3];
+        int ti[NT], tj[NT];
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
+        for (int t = 0; t < NT; ++t) {
             const int idx = tid + t * TT;
             int aa = -1, bb = 0;
             if (idx < ntri) {
@@ -338,13 +352,13 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
             ti[t] = aa;
             tj[t] = bb;
         }
-        float acc[3][16];
+        float acc[NT][16];
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
+        for (int t = 0; t < NT; ++t)
 #pragma unroll
             for (int q = 0; q < 16; ++q) acc[t][q] = 0.f;
         __syncthreads();
-        if (!L.gram) {
+        if constexpr (!GRAM) {
             // C = Y^T Y: patches staged 32 at a time as rows Y[nn][0..LD)
             for (int c0 = 0; c0 < n; c0 += CH) {
                 const int rows = min(CH, n - c0);
@@ -360,7 +374,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                 for (int nn = 0; nn < rows; ++nn) {
                     const float *row = R + nn * LD;
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) {
+                    for (int t = 0; t < NT; ++t) {
                         if (ti[t] >= 0) {
                             const float4 xi = *reinterpret_cast<const float4 *>(row + 4 * ti[t]);
                             const float4 xj = *reinterpret_cast<const float4 *>(row + 4 * tj[t]);
@@ -388,7 +402,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                 for (int l = 0; l < ncol; ++l) {
                     const float *row = R + l * LDq;
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) {
+                    for (int t = 0; t < NT; ++t) {
                         if (ti[t] >= 0) {
                             const float4 xi = *reinterpret_cast<const float4 *>(row + 4 * ti[t]);
                             const float4 xj = *reinterpret_cast<const float4 *>(row + 4 * tj[t]);
@@ -406,7 +420,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
         }
         float *A = R;
 #pragma unroll
-        for (int t = 0; t < 3; ++t)
+        for (int t = 0; t < NT; ++t)
             if (ti[t] >= 0)
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa)
@@ -660,7 +674,7 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                 }
             }
             __syncthreads();
-            if (!L.gram) {
+            if constexpr (!GRAM) {
                 // eigenvectors re-laid as Vt[j][r] (r contiguous, pitch MR): 4 eigenpairs per broadcast LDS.128
                 float *Vt = R + L.oVt;
                 for (int idx = tid; idx < p * (MR / 4); idx += TT)
@@ -673,14 +687,26 @@ __global__ void __launch_bounds__(TT, 5) bayes_kernel(const BayesArgs a) {
                         if (j < p) Vt[j * MR + r] = Z[r * ZSq + j];
                     }
             } else {
-                // Gram trick: Ut[nn][r] at the head of R, then v_r = Y^T u_r / sqrt(n lambda_r) straight into Vt[j][r]
-                float *Ut = R;
-                for (int idx = tid; idx < n * (MR / 4); idx += TT)
-                    reinterpret_cast<float4 *>(Ut)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                // Gram trick: Z[r][nn] -> Ut[nn][r] in place (through registers), then
+                // v_r = Y^T u_r / sqrt(n lambda_r) straight into Vt[j][r]
+                float *Ut = Z;
+                float tz[(MR + TT / 32 - 1) / (TT / 32)][2];
+#pragma unroll
+                for (int rr = 0; rr < (MR + TT / 32 - 1) / (TT / 32); ++rr) {
+                    const int r = warp + rr * (TT / 32);
+                    tz[rr][0] = (r < m && lane < n) ? Z[r * ZSq + lane] : 0.f;
+                    tz[rr][1] = (r < m && lane + 32 < n) ? Z[r * ZSq + lane + 32] : 0.f;
+                }
                 __syncthreads();
-                for (int r = warp; r < m; r += TT / 32)
-                    for (int nn = lane; nn < n; nn += 32) Ut[nn * MR + r] = Z[r * ZSq + nn];
-                __syncthreads();                          // Z is dead from here on: Vt may overlap it
+#pragma unroll
+                for (int rr = 0; rr < (MR + TT / 32 - 1) / (TT / 32); ++rr) {
+                    const int r = warp + rr * (TT / 32);
+                    if (r < MR) {
+                        if (lane < n) Ut[lane * MR + r] = tz[rr][0];
+                        if (lane + 32 < n) Ut[(lane + 32) * MR + r] = tz[rr][1];
+                    }
+                }
+                __syncthreads();
                 float *Vt = R + L.oVt;
                 switch ((m + 7) >> 3) {
                     case 1: gram_map<1>(Vt, Ut, lam, mean, src, pb, FUSED, rstride, n, p, m, tid < p ? col_off(tid, ch) : 0, tid); break;
@@ -786,9 +812,10 @@ int launch_bayes_tridiag(float *pnoisy, const float *pbasic, const unsigned char
     a.P = *p;
     a.L = tri_layout(p->k, p->pt * p->ps * p->ps);
     const size_t smem = (size_t)a.L.total * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(bayes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = a.L.gram ? bayes_kernel<false, true> : bayes_kernel<false, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("vnlb_bayes_filter: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
-    bayes_kernel<false><<<B * p->c, TT, smem, st>>>(a);
+    kern<<<B * p->c, TT, smem, st>>>(a);
     return check_launch("vnlb_bayes_filter(tridiag)");
 }
 
@@ -801,9 +828,10 @@ int launch_bayes_fused(const float *img_noisy, const float *img_basic, const lon
     a.P = *p;
     a.L = tri_layout(p->k, p->pt * p->ps * p->ps);
     const size_t smem = (size_t)a.L.total * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(bayes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = a.L.gram ? bayes_kernel<true, true> : bayes_kernel<true, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("vnlb_bayes_aggregate_fused: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
-    bayes_kernel<true><<<B, TT, smem, st>>>(a);
+    kern<<<B, TT, smem, st>>>(a);
     return check_launch("vnlb_bayes_aggregate_fused");
 }
 
