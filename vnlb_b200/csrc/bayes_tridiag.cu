@@ -79,7 +79,7 @@ static TriLayout tri_layout(int n, int p) {
         L.oX = L.oZ;
         int zsz = MR * L.ZSq;
         if (zsz < n * MR) zsz = n * MR;
-        const int want_rows = n < 32 ? n : 32;
+        const int want_rows = n < 24 ? n : 24;
         if (zsz < want_rows * L.XS) zsz = want_rows * L.XS;
         rsize = L.oZ + zsz;
     }
@@ -246,7 +246,7 @@ __device__ __forceinline__ void gram_map(float *Vt, const float *Ut, const float
 }
 
 template <bool FUSED, bool GRAM>
-__global__ void __launch_bounds__(TT, GRAM ? 6 : 5) bayes_kernel(const BayesArgs a) {
+__global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs a) {
     constexpr int NT = GRAM ? 1 : 3;               // 4x4 tiles of the (covariance | Gram) matrix per thread
     extern __shared__ __align__(16) float sm[];
     const VnlbBayesParams &P = a.P;
