@@ -254,6 +254,13 @@ def update_mask_inds(mask, inds, c, boost=True):
         mask[mt[ok], mh[ok], mw[ok]] = 0
 
 
+def exec_refinement(vals, inds, thresh=2.0):
+    """lib/vnlb/search/refinement.py:15-29 (in place on inds)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ave = np.mean(vals[:, 1:] / vals[:, [1]], 1)
+    inds[ave > thresh] = -1
+
+
 # ----------------------------------------------------------------------------
 # flat areas  (lib/vnlb/utils/flat_areas.py)
 # ----------------------------------------------------------------------------

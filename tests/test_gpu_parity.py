@@ -488,3 +488,19 @@ def test_fast_schedule_is_deterministic_and_serial_equals_overlapped(vb):
     assert outs[0][1] == outs[1][1] == outs[2][1]                 # same groups drawn (hash-based selection)
     assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-3           # float-atomic order only
     assert np.abs(outs[0][0] - outs[2][0]).max() < 1e-3
+
+
+def test_refinement_matches_oracle(vb):
+    from vnlb_b200 import search
+    from vnlb_b200.utils import AttrDict
+    rs = np.random.RandomState(8)
+    vals = np.sort(rs.rand(12, 20).astype(np.float32) * 100, 1)
+    vals[:, 0] = 0
+    vals[3, 2:] *= 50                                           # a row whose neighbours are far worse than its best
+    inds = rs.randint(0, 1000, (12, 20)).astype(np.int64)
+    ref = inds.copy()
+    orc.exec_refinement(vals, ref)
+    bufs = AttrDict(vals=cu(vals), inds=cu(inds))
+    search.exec_refinement(None, bufs, 20.)
+    np.testing.assert_array_equal(bufs.inds.cpu().numpy(), ref)
+    assert (ref[3] == -1).all() and (ref != -1).any()

@@ -70,3 +70,18 @@ def test_synth_matches_oracle_generator():
     assert np.array_equal(synth.synth_video(3, 24, 32), orc.synth_video(3, 24, 32))
     c = synth.synth_video(2, 16, 16)
     assert np.array_equal(synth.add_noise(c, 20.), orc.add_noise(c, 20.))
+
+
+def test_video_io_roundtrip_and_report(tmp_path):
+    from vnlb_b200 import video_io
+    rs = np.random.RandomState(0)
+    vid = rs.randint(0, 256, (3, 3, 10, 12)).astype(np.float32)
+    video_io.save_video_sequence(vid, str(tmp_path / "a"))
+    back = video_io.read_video_sequence(str(tmp_path / "a"))
+    assert back.shape == vid.shape and np.array_equal(back, vid)
+    video_io.save_video_sequence(vid, str(tmp_path / "b"), fmt="%03d.npy")
+    assert np.array_equal(video_io.read_video_sequence(str(tmp_path / "b")), vid)
+    rep = video_io.compare_report(vid + 1, vid, clean=vid)
+    assert rep["Ave Rel. Error"] > 0 and np.isinf(rep["other_psnr"]) and abs(rep["our_psnr"] - 48.13) < 0.01
+    with pytest.raises(FileNotFoundError):
+        video_io.read_video_sequence(str(tmp_path / "none"))

@@ -97,3 +97,13 @@ def exec_search(patches, imgs, flows, mask, bufs, args):
         search_mask.update_mask_inds(mask, vbufs.inds, args.c, boost=args.aggreBoost)
     done = done or (mask.sum().item() == 0)
     return done
+
+
+def exec_refinement(patches, bufs, sigma, thresh=2.0):
+    """lib/vnlb/search/refinement.py:15-29 (disabled in the reference at proc_nl.py:70): rows whose
+    mean distance ratio vals[:,1:]/vals[:,1] exceeds `thresh` are dropped (all their indices set to -1).
+    A few elementwise torch ops on [rows,k]; not on the hot path."""
+    vals = bufs.vals
+    ave_vals = torch.mean(vals[:, 1:] / vals[:, [1]], 1)
+    noupdate = torch.nonzero(ave_vals > thresh)
+    bufs.inds[noupdate] = -1
