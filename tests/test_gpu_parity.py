@@ -494,7 +494,7 @@ def test_refinement_matches_oracle(vb):
     from vnlb_b200 import search
     from vnlb_b200.utils import AttrDict
     rs = np.random.RandomState(8)
-    vals = np.sort(rs.rand(12, 20).astype(np.float32) * 100, 1)
+    vals = np.sort(50 + rs.rand(12, 20).astype(np.float32) * 20, 1)
     vals[:, 0] = 0
     vals[3, 2:] *= 50                                           # a row whose neighbours are far worse than its best
     inds = rs.randint(0, 1000, (12, 20)).astype(np.int64)

@@ -158,16 +158,17 @@ __device__ __forceinline__ float block_max(float v, float *red, int &phase) {
 }
 
 // Wiener filter of `rows` centred patches staged in X (pitch XS): xhat = sum_r coef_r <x, v_r> v_r + mean
-// (bayes_est.py:146-151,51).  MB = number of 8-eigenpair blocks; two threads share a patch when rows <= 64.
+// (bayes_est.py:146-151,51).  MB = number of 8-eigenpair blocks; 4 / 2 / 1 threads share a patch
+// (rows <= 32 / <= 64 / more), each projecting and reconstructing its slice of the patch.
 template <int MB>
 __device__ __forceinline__ void filter_chunk(float *X, const float *Vt, const float *coef, const float *mean, int rows,
                                              int p, int XS, int m, int tid) {
-    const bool two = 2 * rows <= TT;
-    const int row = two ? (tid >> 1) : tid, part = two ? (tid & 1) : 0;
+    const int lsp = (4 * rows <= TT) ? 2 : ((2 * rows <= TT) ? 1 : 0);   // log2(threads per patch): 4, 2 or 1
+    const int row = tid >> lsp, part = tid & ((1 << lsp) - 1);
     const bool on = row < rows;
     float *xr = X + min(row, rows - 1) * XS;
-    const int ph = two ? ((p + 1) >> 1) : p;
-    const int j0 = part * ph, j1 = min(p, j0 + ph);
+    const int ph = (p + (1 << lsp) - 1) >> lsp;
+    const int j0 = min(p, part * ph), j1 = min(p, j0 + ph);
     if (MB == 0) {
         if (on) for (int j = j0; j < j1; ++j) xr[j] = mean[j];
         return;
@@ -189,7 +190,8 @@ __device__ __forceinline__ void filter_chunk(float *X, const float *Vt, const fl
     }
 #pragma unroll
     for (int r = 0; r < 8 * MB; ++r) {
-        if (two) zc[r] += __shfl_xor_sync(0xffffffffu, zc[r], 1);
+        if (lsp >= 1) zc[r] += __shfl_xor_sync(0xffffffffu, zc[r], 1);
+        if (lsp >= 2) zc[r] += __shfl_xor_sync(0xffffffffu, zc[r], 2);
         zc[r] *= (r < m) ? coef[r] : 0.f;
     }
     for (int j = j0; j < j1; ++j) {

@@ -92,7 +92,7 @@ def _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap,
             nrounds += 1
             if q == 0:
                 continue
-            tok = tm.start("search") if tm else None
+            tok = tm.start("search_s%d" % args.step) if tm else None
             search.exec_sim_search_burst(srch_img, qinds[:q], vals[:q], inds[:q], flows, args.sigma, args)
             if tm:
                 tm.stop(tok)
@@ -101,7 +101,7 @@ def _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap,
             done_search[buf].record(sA)
         with torch.cuda.stream(sB):
             sB.wait_event(done_search[buf])
-            tok = tm.start("bayes") if tm else None
+            tok = tm.start("bayes_s%d" % args.step) if tm else None
             deno.bayes_aggregate_fused(images, inds[:q], args)
             if tm:
                 tm.stop(tok)
@@ -164,7 +164,7 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
         rows = AttrDict(noisy=ws.noisy[:q], basic=ws.basic[:q], flat=ws.flat[:q], clean=None)
         vals, inds = ws.vals[:q], ws.inds[:q]
         tm = L.timer
-        tok = tm.start("search") if tm else None
+        tok = tm.start("search_s%d" % args.step) if tm else None
         search.exec_sim_search_burst(srch_img, ws.qinds[:q], vals, inds, flows, args.sigma, args)
         if tm:
             tm.stop(tok)
@@ -173,7 +173,7 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
         if fused:
             if tm:
                 tm.stop(tok)
-                tok = tm.start("bayes")
+                tok = tm.start("bayes_s%d" % args.step)
             deno.bayes_aggregate_fused(images, inds, args)
             if tm:
                 tm.stop(tok)
@@ -185,7 +185,7 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
         update_flat_patch(rows, args, inds)
         if tm:
             tm.stop(tok)
-            tok = tm.start("bayes")
+            tok = tm.start("bayes_s%d" % args.step)
         deno.denoise(rows, args, args.deno, inds)
         if tm:
             tm.stop(tok)
