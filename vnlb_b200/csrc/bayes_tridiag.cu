@@ -178,14 +178,17 @@ __device__ __forceinline__ void filter_chunk(float *X, const float *Vt, const fl
     for (int r = 0; r < 8 * MB; ++r) zc[r] = 0.f;
     for (int j = j0; j < j1; ++j) {
         const float xv = xr[j];
+        const float2 xd = make_float2(xv, xv);
         const float4 *vt = reinterpret_cast<const float4 *>(Vt + j * MR);
 #pragma unroll
         for (int b = 0; b < MB; ++b) {
             const float4 f = vt[2 * b], h = vt[2 * b + 1];
-            zc[8 * b + 0] = fmaf(xv, f.x, zc[8 * b + 0]); zc[8 * b + 1] = fmaf(xv, f.y, zc[8 * b + 1]);
-            zc[8 * b + 2] = fmaf(xv, f.z, zc[8 * b + 2]); zc[8 * b + 3] = fmaf(xv, f.w, zc[8 * b + 3]);
-            zc[8 * b + 4] = fmaf(xv, h.x, zc[8 * b + 4]); zc[8 * b + 5] = fmaf(xv, h.y, zc[8 * b + 5]);
-            zc[8 * b + 6] = fmaf(xv, h.z, zc[8 * b + 6]); zc[8 * b + 7] = fmaf(xv, h.w, zc[8 * b + 7]);
+            const float2 z0 = __ffma2_rn(xd, make_float2(f.x, f.y), make_float2(zc[8 * b + 0], zc[8 * b + 1]));
+            const float2 z1 = __ffma2_rn(xd, make_float2(f.z, f.w), make_float2(zc[8 * b + 2], zc[8 * b + 3]));
+            const float2 z2 = __ffma2_rn(xd, make_float2(h.x, h.y), make_float2(zc[8 * b + 4], zc[8 * b + 5]));
+            const float2 z3 = __ffma2_rn(xd, make_float2(h.z, h.w), make_float2(zc[8 * b + 6], zc[8 * b + 7]));
+            zc[8 * b + 0] = z0.x; zc[8 * b + 1] = z0.y; zc[8 * b + 2] = z1.x; zc[8 * b + 3] = z1.y;
+            zc[8 * b + 4] = z2.x; zc[8 * b + 5] = z2.y; zc[8 * b + 6] = z3.x; zc[8 * b + 7] = z3.y;
         }
     }
 #pragma unroll
@@ -226,10 +229,13 @@ __device__ __forceinline__ void gram_map(float *Vt, const float *Ut, const float
 #pragma unroll
         for (int b = 0; b < MB; ++b) {
             const float4 f = ut[2 * b], h = ut[2 * b + 1];
-            acc[8 * b + 0] = fmaf(y, f.x, acc[8 * b + 0]); acc[8 * b + 1] = fmaf(y, f.y, acc[8 * b + 1]);
-            acc[8 * b + 2] = fmaf(y, f.z, acc[8 * b + 2]); acc[8 * b + 3] = fmaf(y, f.w, acc[8 * b + 3]);
-            acc[8 * b + 4] = fmaf(y, h.x, acc[8 * b + 4]); acc[8 * b + 5] = fmaf(y, h.y, acc[8 * b + 5]);
-            acc[8 * b + 6] = fmaf(y, h.z, acc[8 * b + 6]); acc[8 * b + 7] = fmaf(y, h.w, acc[8 * b + 7]);
+            const float2 yd = make_float2(y, y);
+            const float2 z0 = __ffma2_rn(yd, make_float2(f.x, f.y), make_float2(acc[8 * b + 0], acc[8 * b + 1]));
+            const float2 z1 = __ffma2_rn(yd, make_float2(f.z, f.w), make_float2(acc[8 * b + 2], acc[8 * b + 3]));
+            const float2 z2 = __ffma2_rn(yd, make_float2(h.x, h.y), make_float2(acc[8 * b + 4], acc[8 * b + 5]));
+            const float2 z3 = __ffma2_rn(yd, make_float2(h.z, h.w), make_float2(acc[8 * b + 6], acc[8 * b + 7]));
+            acc[8 * b + 0] = z0.x; acc[8 * b + 1] = z0.y; acc[8 * b + 2] = z1.x; acc[8 * b + 3] = z1.y;
+            acc[8 * b + 4] = z2.x; acc[8 * b + 5] = z2.y; acc[8 * b + 6] = z3.x; acc[8 * b + 7] = z3.y;
         }
     }
     float4 *vt = reinterpret_cast<float4 *>(Vt + tid * MR);
@@ -380,12 +386,16 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                         if (ti[t] >= 0) {
                             const float4 xi = *reinterpret_cast<const float4 *>(row + 4 * ti[t]);
                             const float4 xj = *reinterpret_cast<const float4 *>(row + 4 * tj[t]);
-                            const float a4[4] = {xi.x, xi.y, xi.z, xi.w}, b4[4] = {xj.x, xj.y, xj.z, xj.w};
+                            const float a4[4] = {xi.x, xi.y, xi.z, xi.w};
+                            const float2 blo = make_float2(xj.x, xj.y), bhi = make_float2(xj.z, xj.w);
 #pragma unroll
-                            for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-                                for (int bb = 0; bb < 4; ++bb)
-                                    acc[t][aa * 4 + bb] = fmaf(a4[aa], b4[bb], acc[t][aa * 4 + bb]);
+                            for (int aa = 0; aa < 4; ++aa) {   // packed FP32 FMAs (FFMA2): bit-identical to 4 scalar FMAs
+                                const float2 ad = make_float2(a4[aa], a4[aa]);
+                                const float2 r0 = __ffma2_rn(ad, blo, make_float2(acc[t][aa * 4 + 0], acc[t][aa * 4 + 1]));
+                                const float2 r1 = __ffma2_rn(ad, bhi, make_float2(acc[t][aa * 4 + 2], acc[t][aa * 4 + 3]));
+                                acc[t][aa * 4 + 0] = r0.x; acc[t][aa * 4 + 1] = r0.y;
+                                acc[t][aa * 4 + 2] = r1.x; acc[t][aa * 4 + 3] = r1.y;
+                            }
                         }
                     }
                 }
@@ -408,12 +418,16 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                         if (ti[t] >= 0) {
                             const float4 xi = *reinterpret_cast<const float4 *>(row + 4 * ti[t]);
                             const float4 xj = *reinterpret_cast<const float4 *>(row + 4 * tj[t]);
-                            const float a4[4] = {xi.x, xi.y, xi.z, xi.w}, b4[4] = {xj.x, xj.y, xj.z, xj.w};
+                            const float a4[4] = {xi.x, xi.y, xi.z, xi.w};
+                            const float2 blo = make_float2(xj.x, xj.y), bhi = make_float2(xj.z, xj.w);
 #pragma unroll
-                            for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-                                for (int bb = 0; bb < 4; ++bb)
-                                    acc[t][aa * 4 + bb] = fmaf(a4[aa], b4[bb], acc[t][aa * 4 + bb]);
+                            for (int aa = 0; aa < 4; ++aa) {   // packed FP32 FMAs (FFMA2): bit-identical to 4 scalar FMAs
+                                const float2 ad = make_float2(a4[aa], a4[aa]);
+                                const float2 r0 = __ffma2_rn(ad, blo, make_float2(acc[t][aa * 4 + 0], acc[t][aa * 4 + 1]));
+                                const float2 r1 = __ffma2_rn(ad, bhi, make_float2(acc[t][aa * 4 + 2], acc[t][aa * 4 + 3]));
+                                acc[t][aa * 4 + 0] = r0.x; acc[t][aa * 4 + 1] = r0.y;
+                                acc[t][aa * 4 + 2] = r1.x; acc[t][aa * 4 + 3] = r1.y;
+                            }
                         }
                     }
                 }
@@ -463,22 +477,25 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
             float yi = 0.f;
             if (active) {
                 const float *ar = A + i * LDq;
-                float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+                float2 y01 = make_float2(0.f, 0.f), y23 = make_float2(0.f, 0.f);   // packed FP32 FMAs (FFMA2, sm_100)
                 int j = jb;
                 for (; j + 4 < LDq; j += 8) {
                     const float4 a4 = *reinterpret_cast<const float4 *>(ar + j);
                     const float4 b4 = *reinterpret_cast<const float4 *>(ar + j + 4);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j);
                     const float4 u4 = *reinterpret_cast<const float4 *>(v + j + 4);
-                    y0 = fmaf(a4.x, v4.x, y0); y1 = fmaf(a4.y, v4.y, y1); y2 = fmaf(a4.z, v4.z, y2); y3 = fmaf(a4.w, v4.w, y3);
-                    y0 = fmaf(b4.x, u4.x, y0); y1 = fmaf(b4.y, u4.y, y1); y2 = fmaf(b4.z, u4.z, y2); y3 = fmaf(b4.w, u4.w, y3);
+                    y01 = __ffma2_rn(make_float2(a4.x, a4.y), make_float2(v4.x, v4.y), y01);
+                    y23 = __ffma2_rn(make_float2(a4.z, a4.w), make_float2(v4.z, v4.w), y23);
+                    y01 = __ffma2_rn(make_float2(b4.x, b4.y), make_float2(u4.x, u4.y), y01);
+                    y23 = __ffma2_rn(make_float2(b4.z, b4.w), make_float2(u4.z, u4.w), y23);
                 }
                 if (j < LDq) {
                     const float4 a4 = *reinterpret_cast<const float4 *>(ar + j);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j);
-                    y0 = fmaf(a4.x, v4.x, y0); y1 = fmaf(a4.y, v4.y, y1); y2 = fmaf(a4.z, v4.z, y2); y3 = fmaf(a4.w, v4.w, y3);
+                    y01 = __ffma2_rn(make_float2(a4.x, a4.y), make_float2(v4.x, v4.y), y01);
+                    y23 = __ffma2_rn(make_float2(a4.z, a4.w), make_float2(v4.z, v4.w), y23);
                 }
-                yi = (y0 + y1) + (y2 + y3);
+                yi = (y01.x + y01.y) + (y23.x + y23.y);
             }
             float wi = tau * yi;
             const float s = block_sum(active ? wi * vi : 0.f, red, phase);
@@ -487,25 +504,28 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
             __syncthreads();
             if (active) {
                 float *ar = A + i * LDq;
-                const float nvi = -vi, nwi = -wi;
+                const float2 nvi = make_float2(-vi, -vi), nwi = make_float2(-wi, -wi);
                 int j = jb;
                 for (; j + 4 < LDq; j += 8) {
                     float4 a4 = *reinterpret_cast<float4 *>(ar + j);
                     float4 b4 = *reinterpret_cast<float4 *>(ar + j + 4);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j), w4 = *reinterpret_cast<const float4 *>(w + j);
                     const float4 u4 = *reinterpret_cast<const float4 *>(v + j + 4), z4 = *reinterpret_cast<const float4 *>(w + j + 4);
-                    a4.x = fmaf(nvi, w4.x, fmaf(nwi, v4.x, a4.x)); a4.y = fmaf(nvi, w4.y, fmaf(nwi, v4.y, a4.y));
-                    a4.z = fmaf(nvi, w4.z, fmaf(nwi, v4.z, a4.z)); a4.w = fmaf(nvi, w4.w, fmaf(nwi, v4.w, a4.w));
-                    b4.x = fmaf(nvi, z4.x, fmaf(nwi, u4.x, b4.x)); b4.y = fmaf(nvi, z4.y, fmaf(nwi, u4.y, b4.y));
-                    b4.z = fmaf(nvi, z4.z, fmaf(nwi, u4.z, b4.z)); b4.w = fmaf(nvi, z4.w, fmaf(nwi, u4.w, b4.w));
+                    { const float2 lo = __ffma2_rn(nvi, make_float2(w4.x, w4.y), __ffma2_rn(nwi, make_float2(v4.x, v4.y), make_float2(a4.x, a4.y)));
+                      const float2 hi = __ffma2_rn(nvi, make_float2(w4.z, w4.w), __ffma2_rn(nwi, make_float2(v4.z, v4.w), make_float2(a4.z, a4.w)));
+                      a4 = make_float4(lo.x, lo.y, hi.x, hi.y); }
+                    { const float2 lo = __ffma2_rn(nvi, make_float2(z4.x, z4.y), __ffma2_rn(nwi, make_float2(u4.x, u4.y), make_float2(b4.x, b4.y)));
+                      const float2 hi = __ffma2_rn(nvi, make_float2(z4.z, z4.w), __ffma2_rn(nwi, make_float2(u4.z, u4.w), make_float2(b4.z, b4.w)));
+                      b4 = make_float4(lo.x, lo.y, hi.x, hi.y); }
                     *reinterpret_cast<float4 *>(ar + j) = a4;
                     *reinterpret_cast<float4 *>(ar + j + 4) = b4;
                 }
                 if (j < LDq) {
                     float4 a4 = *reinterpret_cast<float4 *>(ar + j);
                     const float4 v4 = *reinterpret_cast<const float4 *>(v + j), w4 = *reinterpret_cast<const float4 *>(w + j);
-                    a4.x = fmaf(nvi, w4.x, fmaf(nwi, v4.x, a4.x)); a4.y = fmaf(nvi, w4.y, fmaf(nwi, v4.y, a4.y));
-                    a4.z = fmaf(nvi, w4.z, fmaf(nwi, v4.z, a4.z)); a4.w = fmaf(nvi, w4.w, fmaf(nwi, v4.w, a4.w));
+                    { const float2 lo = __ffma2_rn(nvi, make_float2(w4.x, w4.y), __ffma2_rn(nwi, make_float2(v4.x, v4.y), make_float2(a4.x, a4.y)));
+                      const float2 hi = __ffma2_rn(nvi, make_float2(w4.z, w4.w), __ffma2_rn(nwi, make_float2(v4.z, v4.w), make_float2(a4.z, a4.w)));
+                      a4 = make_float4(lo.x, lo.y, hi.x, hi.y); }
                     *reinterpret_cast<float4 *>(ar + j) = a4;
                 }
             }
