@@ -668,7 +668,11 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 }
                 z[r] = 1.f;
                 const float sc = rsqrtf(nrm);
-                for (int i = 0; i < qd; ++i) z[i] *= sc;
+                if (nrm < 3.0e38f && sc > 0.f) {
+                    for (int i = 0; i < qd; ++i) z[i] *= sc;
+                } else {                                 // overflow guard (never seen): fall back to the twist basis vector
+                    for (int i = 0; i < qd; ++i) z[i] = (i == r) ? 1.f : 0.f;
+                }
             }
             __syncthreads();
 
