@@ -62,7 +62,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: call at the start / end of the timed region."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if self.proc is None:
             return None
         self.proc.terminate()
@@ -72,7 +76,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[first:last] if (last is None or last > first) else self.rows
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -182,24 +187,27 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    # the clock sampler starts before the warm-up so that spawning nvidia-smi never lands in a timed region;
+    # only the samples taken during the timed regions are reported
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
     # ---- warm-up ----
     stats = {}
     for _ in range(args.warmup):
         call(noisy_dev, stats)
 
     # ---- device-resident throughput (`value`) ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = _lib.launches
     result = {}
 
     def step_dev():
         result["deno"], result["basic"], _ = call(noisy_dev)
 
+    s_first = sampler.mark()
     ms = timed(step_dev, args.steps)
     launches = (_lib.launches - l0) // max(args.steps, 1)
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the public API with host buffers (`e2e`) ----
     def step_e2e():
@@ -209,6 +217,7 @@ def run_ours(args):
         torch.cuda.current_stream().synchronize()
 
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop(s_first, sampler.mark()) if rank == 0 else None
 
     # ---- per-stage device time -> roofline of the dominant kernel (rank 0 timing, max over ranks skipped) ----
     _lib.timer = _lib.StageTimer()
@@ -222,7 +231,8 @@ def run_ours(args):
         mine = torch.tensor([float(sum(ngroups)), float(sum(v["ms"] for v in stage.values()))], device=device)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
-        per_rank = dict(groups=[int(a[0].item()) for a in allr], stage_ms=[round(float(a[1].item()), 1) for a in allr])
+        per_rank = dict(groups=[int(a[0].item()) for a in allr], stage_ms=[round(float(a[1].item()), 1) for a in allr],
+                        allreduce_ms_rank0=[round(x, 2) for x in st2.get("allreduce_ms", [])])
 
     if rank == 0:
         hbm_peak, peak_kind = load_peaks()

@@ -122,6 +122,10 @@ int vnlb_mask_update(int8_t *mask, const int64_t *inds, int B, int K, int T, int
  * draws beyond `cap` are dropped (they stay set in the mask).  counters:
  * uint32 [2], zeroed by the caller. */
 int vnlb_count_mask(const int8_t *mask, int T, int H, int W, uint32_t *counters, void *stream);
+/* vnlb_pad_queries turns the rows of qinds beyond min(counters[1], cap) into invalid queries (-1,-1,-1):
+ * vnlb_search_topk answers them with all -1 rows, which every later kernel skips, so a whole round can be
+ * enqueued with `cap` rows before the host knows how many were drawn. */
+int vnlb_pad_queries(int64_t *qinds, const uint32_t *counters, int cap, void *stream);
 int vnlb_select_queries(int8_t *mask, int T, int H, int W, double prob, uint32_t seed,
                         uint32_t round, int64_t *qinds, int cap, uint32_t *counters, void *stream);
 

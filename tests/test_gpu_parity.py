@@ -488,6 +488,15 @@ def test_fast_schedule_is_deterministic_and_serial_equals_overlapped(vb):
     assert outs[0][1] == outs[1][1] == outs[2][1]                 # same groups drawn (hash-based selection)
     assert np.abs(outs[0][0] - outs[1][0]).max() < 1e-3           # float-atomic order only
     assert np.abs(outs[0][0] - outs[2][0]).max() < 1e-3
+    # the default (host-sync-free) rounds: deterministic too, same PSNR band
+    res = []
+    for _ in range(2):
+        st = {}
+        deno, _, _ = vb.denoise(noisy, sigma, schedule="fast", verbose=False, stats=st)
+        res.append((deno.cpu().numpy(), st["ngroups"]))
+    assert res[0][1] == res[1][1] and np.abs(res[0][0] - res[1][0]).max() < 1e-3
+    clean = orc.synth_video(T, H, W, 2)
+    assert abs(orc.compute_psnrs(res[0][0], clean).mean() - orc.compute_psnrs(outs[0][0], clean).mean()) < 0.1
 
 
 def test_refinement_matches_oracle(vb):

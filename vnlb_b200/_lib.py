@@ -35,7 +35,7 @@ class BayesParams(ctypes.Structure):
 EXPORTS = [
     "vnlb_last_error", "vnlb_version", "vnlb_rgb2yuv", "vnlb_yuv2rgb", "vnlb_init_mask",
     "vnlb_search_workspace_bytes", "vnlb_search_topk", "vnlb_fill_patches", "vnlb_mask_update",
-    "vnlb_count_mask", "vnlb_select_queries",
+    "vnlb_count_mask", "vnlb_select_queries", "vnlb_pad_queries",
     "vnlb_flat_areas", "vnlb_bayes_workspace_bytes", "vnlb_bayes_filter", "vnlb_bayes_fused_supported", "vnlb_bayes_aggregate_fused", "vnlb_aggregate",
     "vnlb_normalize",
 ]
@@ -63,6 +63,7 @@ lib.vnlb_fill_patches.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i,
 lib.vnlb_mask_update.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]
 lib.vnlb_count_mask.argtypes = [_vp, _i, _i, _i, _vp, _vp]
 lib.vnlb_select_queries.argtypes = [_vp, _i, _i, _i, ctypes.c_double, ctypes.c_uint32, ctypes.c_uint32, _vp, _i, _vp, _vp]
+lib.vnlb_pad_queries.argtypes = [_vp, _vp, _i, _vp]
 lib.vnlb_flat_areas.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]
 lib.vnlb_bayes_workspace_bytes.argtypes = [_i, ctypes.POINTER(BayesParams)]
 lib.vnlb_bayes_filter.argtypes = [_vp, _vp, _vp, _vp, _i, ctypes.POINTER(BayesParams), _vp, _vp, _sz, _vp]

@@ -166,6 +166,14 @@ __global__ void select_queries_kernel(int8_t *__restrict__ mask, int T, int H, i
     }
 }
 
+// rows of qinds beyond the number drawn become invalid queries (t = -1): lets every kernel of a round run
+// with a fixed grid of `cap` rows, so the host never has to wait for the round size
+__global__ void pad_queries_kernel(long long *__restrict__ qinds, const unsigned int *__restrict__ counters, int cap) {
+    const unsigned int n = min(counters[1], (unsigned)cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x)
+        if ((unsigned)i >= n) { qinds[3 * (long long)i] = -1; qinds[3 * (long long)i + 1] = -1; qinds[3 * (long long)i + 2] = -1; }
+}
+
 }  // namespace vnlb
 
 using namespace vnlb;
@@ -230,6 +238,12 @@ extern "C" int vnlb_select_queries(int8_t *mask, int T, int H, int W, double pro
     select_queries_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, T, H, W, thresh, seed, round,
                                                                              (long long *)qinds, cap, counters);
     return check_launch("vnlb_select_queries");
+}
+
+extern "C" int vnlb_pad_queries(int64_t *qinds, const uint32_t *counters, int cap, void *stream) {
+    VNLB_REQUIRE(qinds && counters && cap > 0, "vnlb_pad_queries: bad argument");
+    pad_queries_kernel<<<div_up(cap, 256), 256, 0, (cudaStream_t)stream>>>((long long *)qinds, counters, cap);
+    return check_launch("vnlb_pad_queries");
 }
 
 extern "C" int vnlb_mask_update(int8_t *mask, const int64_t *inds, int B, int K, int T, int C, int H, int W,

@@ -67,7 +67,14 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
         dflows = prepare_flows(flows, noisy.shape, device)
 
         def reduce_fn(images):
+            if stats is None:
+                allreduce_accumulators(images, group)
+                return
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             allreduce_accumulators(images, group)
+            e1.record()
+            stats.setdefault("allreduce_events", []).append((e0, e1))
 
         basic = None
         for step in (0, 1):
@@ -82,4 +89,6 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
                 basic = images["deno"].clone()
         deno = images["deno"]
         torch.cuda.synchronize(device)
+        if stats is not None and "allreduce_events" in stats:
+            stats["allreduce_ms"] = [a.elapsed_time(b) for a, b in stats.pop("allreduce_events")]
     return deno, basic, clock.toc()

@@ -45,6 +45,8 @@ class _Workspace:
             ws.inds2 = [torch.empty((cap, k), dtype=torch.int64, device=device) for _ in range(2)]
             ws.qinds2 = [torch.empty((cap, 3), dtype=torch.int64, device=device) for _ in range(2)]
             ws.vals, ws.inds, ws.qinds = ws.vals2[0], ws.inds2[0], ws.qinds2[0]
+            ws.counters4 = torch.zeros((4, 2), dtype=torch.int32, device=device)
+            ws.host4 = torch.zeros((4, 2), dtype=torch.int32).pin_memory()
             ws.search_stream = torch.cuda.Stream(device=device)
             ws.bayes_stream = torch.cuda.Stream(device=device)
             ws.counters = torch.zeros((2,), dtype=torch.int32, device=device)
@@ -114,6 +116,77 @@ def _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap,
     return nproc, nrounds, nmask0
 
 
+def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed, est_mask):
+    """Like _rounds_overlapped, but the host never waits for the GPU inside the loop: every kernel of a
+    round is enqueued with `cap` rows (rows beyond the number actually drawn are padded to invalid queries
+    and skipped on the device), the round size is read back two rounds late from a ring of pinned counters,
+    and the draw probability is computed from that (stale, hence conservative) count.  The loop ends when a
+    read-back says the mask is empty; the one or two extra rounds already enqueued are no-ops."""
+    t, c, h, w = images.shape
+    main = torch.cuda.current_stream()
+    sA, sB = ws.search_stream, ws.bayes_stream
+    sA.wait_stream(main)
+    sB.wait_stream(main)
+    done_search, done_bayes, copied = [None, None], [None, None], [None] * 4
+    nproc, nrounds, nmask0 = 0, 0, None
+    remaining = int(est_mask)            # until the first read-back: analytic size of the lattice
+    qmin = min(qmin, max(296, remaining // 64))
+    tm = L.timer
+    r = 0
+    while True:
+        buf, slot = r & 1, r & 3
+        target = min(cap, max(qmin, int(remaining * frac)))
+        prob = 1.0 if remaining <= target else target / remaining * 0.97
+        with torch.cuda.stream(sA):
+            st = L.stream_ptr()
+            cnt = ws.counters4[slot]
+            cnt.zero_()
+            if done_bayes[buf] is not None:
+                sA.wait_event(done_bayes[buf])                               # round r-2 is done with this buffer
+            qinds, vals, inds = ws.qinds2[buf], ws.vals2[buf], ws.inds2[buf]
+            L.check(L.lib.vnlb_count_mask(L.ptr(mask), t, h, w, L.ptr(cnt), st), "vnlb_count_mask")
+            L.check(L.lib.vnlb_select_queries(L.ptr(mask), t, h, w, prob, seed, r, L.ptr(qinds), cap, L.ptr(cnt), st),
+                    "vnlb_select_queries")
+            L.check(L.lib.vnlb_pad_queries(L.ptr(qinds), L.ptr(cnt), cap, st), "vnlb_pad_queries")
+            ws.host4[slot].copy_(cnt, non_blocking=True)
+            copied[slot] = torch.cuda.Event()
+            copied[slot].record(sA)
+            tok = tm.start("search_s%d" % args.step) if tm else None
+            search.exec_sim_search_burst(srch_img, qinds, vals, inds, flows, args.sigma, args)
+            if tm:
+                tm.stop(tok)
+            search_mask.update_mask_inds(mask, inds, c, boost=args.aggreBoost)
+            done_search[buf] = torch.cuda.Event()
+            done_search[buf].record(sA)
+        with torch.cuda.stream(sB):
+            sB.wait_event(done_search[buf])
+            tok = tm.start("bayes_s%d" % args.step) if tm else None
+            deno.bayes_aggregate_fused(images, inds, args)
+            if tm:
+                tm.stop(tok)
+            done_bayes[buf] = torch.cuda.Event()
+            done_bayes[buf].record(sB)
+        r += 1
+        if r >= 2:                       # read back round r-2 (long finished: no stall in steady state)
+            old = (r - 2) & 3
+            copied[old].synchronize()
+            rem_old, nsel = int(ws.host4[old][0]), min(int(ws.host4[old][1]), cap)
+            if nmask0 is None:
+                nmask0 = rem_old
+            nproc += nsel
+            nrounds += 1
+            if rem_old == 0:
+                break
+            remaining = max(rem_old - nsel, 1)
+    # the last enqueued round (r-1) drew nothing or its groups are counted here
+    last = (r - 1) & 3
+    copied[last].synchronize()
+    nproc += min(int(ws.host4[last][1]), cap)
+    main.wait_stream(sA)
+    main.wait_stream(sB)
+    return nproc, nrounds, nmask0
+
+
 def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
     """One VNLB step with the throughput schedule (same contract as proc_nl)."""
     dev = images.device
@@ -132,8 +205,16 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
     if srch_img is None:
         raise ValueError("uknown search image [%s]" % args.srch_img)
     nproc, nrounds, nmask0 = 0, 0, None
-    if fused and bool(args.get("fast_overlap", True)):
-        nproc, nrounds, nmask0 = _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed)
+    overlap = args.get("fast_overlap", "async")
+    if fused and overlap:
+        if overlap == "async":
+            bands = [(0, h)] if y_range is None else ([y_range] if isinstance(y_range[0], int) else list(y_range))
+            rows = sum(min(b, h - args.ps + 1) - a for a, b in bands)
+            est = (t - args.pt + 1) * max(rows, 1) * (w - args.ps + 1) // (args.procStep ** 2)
+            nproc, nrounds, nmask0 = _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed,
+                                                   est + est // 8)
+        else:
+            nproc, nrounds, nmask0 = _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed)
         finish_step(images, args, reduce_fn)
         if stats is not None:
             stats.setdefault("ngroups", []).append(nproc)
