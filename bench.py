@@ -41,54 +41,48 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region, read through NVML from the benchmark
+    thread itself right after each step is enqueued/finished (a few microseconds per query).  A background
+    poller (nvidia-smi -lms or an NVML thread) was measured to cause sporadic +50..100 ms stalls of single
+    steps on this box, so no second thread is used."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.ok, self.max_mhz = index, [], False, 0.0
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.sample()
+            self.rows.clear()
         except Exception:
-            self.proc = None
+            self.ok = False
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def mark(self):
-        """Index of the next sample: call at the start / end of the timed region."""
-        return len(self.rows)
-
-    def stop(self, first=0, last=None):
-        if self.proc is None:
-            return None
-        self.proc.terminate()
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
         try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], 0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = self.rows[first:last] if (last is None or last > first) else self.rows
-        for r in rows:
+            mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
-                pass
-        if not sm:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            self.rows.append((mhz, mask))
+        except Exception:
+            pass
+
+    def summary(self):
+        if not self.ok or not self.rows:
             return None
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        reasons = sorted({name for _, m in self.rows for bit, name in self.REASONS.items() if m & bit})
+        return dict(sm_mhz=float(np.median([r[0] for r in self.rows])), sm_max_mhz=self.max_mhz, reasons=reasons,
+                    samples=len(self.rows), source="nvml, sampled while the timed steps execute")
 
 
 def make_video(n_gpus):
@@ -174,15 +168,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    per_step = {}
+
+    def timed(fn, steps, tag):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            evs[i + 1].record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        per_step[tag] = [round(evs[i].elapsed_time(evs[i + 1]), 1) for i in range(steps)]
+        ms = torch.tensor([evs[0].elapsed_time(evs[steps])], device=device)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
@@ -193,20 +190,22 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
 
-    # ---- warm-up ----
-    stats = {}
-    for _ in range(args.warmup):
-        call(noisy_dev, stats)
-
-    # ---- device-resident throughput (`value`) ----
-    l0 = _lib.launches
     result = {}
 
     def step_dev():
         result["deno"], result["basic"], _ = call(noisy_dev)
 
-    s_first = sampler.mark()
-    ms = timed(step_dev, args.steps)
+    # ---- warm-up: the same step as the timed one, so kernels are loaded and the caching allocator has
+    #      reached its steady state (a first-time cudaMalloc inside a step costs 50-100 ms) ----
+    for _ in range(args.warmup):
+        step_dev()
+
+    # ---- device-resident throughput (`value`) ----
+    l0 = _lib.launches
+
+    if rank == 0:   # sample the clocks every 64th kernel launch of the timed steps: the GPU is busy at those moments
+        _lib.on_launch = lambda n: sampler.sample() if n % 64 == 0 else None
+    ms = timed(step_dev, args.steps, "value")
     launches = (_lib.launches - l0) // max(args.steps, 1)
 
     # ---- end to end through the public API with host buffers (`e2e`) ----
@@ -216,8 +215,11 @@ def run_ours(args):
             out_pin.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
-    ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop(s_first, sampler.mark()) if rank == 0 else None
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps, "e2e")
+    _lib.on_launch = None
+    clocks = sampler.summary() if rank == 0 else None
 
     # ---- per-stage device time -> roofline of the dominant kernel (rank 0 timing, max over ranks skipped) ----
     _lib.timer = _lib.StageTimer()
@@ -300,7 +302,7 @@ def run_ours(args):
                      h2d_bytes_per_step=int(noisy.nbytes) * max(world, 1), d2h_bytes_per_step=int(noisy.nbytes)),
             gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
             stages_ms={k: round(v["ms"], 3) for k, v in stage.items()}, groups_per_step=ngroups, psnr=psnr,
-            rounds=st2.get("nrounds"), per_rank=per_rank)
+            rounds=st2.get("nrounds"), per_rank=per_rank, per_step_ms_rank0=per_step)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -310,7 +312,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -101,9 +101,14 @@ class StageTimer:
 timer = None
 
 
+on_launch = None   # optional callable(launch_count): bench.py samples NVML clocks from it while the GPU is busy
+
+
 def check(rc, what):
     global launches
     launches += 1
+    if on_launch is not None:
+        on_launch(launches)
     if rc != OK:
         msg = lib.vnlb_last_error().decode()
         if rc == ERR_BAD_ARG:
