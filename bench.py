@@ -171,6 +171,15 @@ def run_ours(args):
     per_step = {}
 
     def timed(fn, steps, tag):
+        import gc
+        gc.collect()
+        gc.disable()        # a full collection of the interpreter heap (~100 ms) inside a step is a host stall, not GPU time
+        try:
+            return _timed(fn, steps, tag)
+        finally:
+            gc.enable()
+
+    def _timed(fn, steps, tag):
         barrier()
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         evs[0].record()
@@ -233,7 +242,11 @@ def run_ours(args):
         mine = torch.tensor([float(sum(ngroups)), float(sum(v["ms"] for v in stage.values()))], device=device)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
+        mine_steps = torch.tensor(per_step["value"], device=device, dtype=torch.float32)
+        all_steps = [torch.zeros_like(mine_steps) for _ in range(world)]
+        dist.all_gather(all_steps, mine_steps)
         per_rank = dict(groups=[int(a[0].item()) for a in allr], stage_ms=[round(float(a[1].item()), 1) for a in allr],
+                        value_step_ms=[[round(float(x), 1) for x in a.tolist()] for a in all_steps],
                         allreduce_ms_rank0=[round(x, 2) for x in st2.get("allreduce_ms", [])])
 
     if rank == 0:

@@ -41,6 +41,20 @@ def test_snake_partition_is_a_partition():
         assert sorted(rows) == list(range(h - 6))
 
 
+def test_weighted_partition_balances_and_covers():
+    from vnlb_b200.dist import partition_rows_weighted
+    rs = np.random.RandomState(0)
+    for h, world in [(480, 2), (3840, 8), (64, 8)]:
+        w = torch.from_numpy(rs.rand(h).astype(np.float32) * (1 + 4 * (np.arange(h) > h // 2)))
+        bands = [partition_rows_weighted(w, 7, world, r) for r in range(world)]
+        assert bands[0][0] == 0 and bands[-1][1] == h
+        for a, b in zip(bands[:-1], bands[1:]):
+            assert a[1] == b[0] and a[1] > a[0]
+        if h > 400:
+            sums = [float(w[a:min(b, h - 6)].sum()) for a, b in bands]
+            assert max(sums) / (sum(sums) / world) < 1.05
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

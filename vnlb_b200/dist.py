@@ -41,6 +41,25 @@ def partition_rows_snake(h, ps, world_size, rank):
     return [a, b]
 
 
+def partition_rows_weighted(weights, ps, world_size, rank):
+    """One contiguous band per rank with (nearly) equal total weight; `weights` [H] = groups per reference
+    row observed in the previous step (identical on every rank).  Fewer band borders than the snake
+    partition and balanced on the actual content."""
+    h = int(weights.shape[0])
+    valid = h - ps + 1
+    w = weights[:valid].double() + 1e-3                    # every row keeps a little weight
+    cum = torch.cumsum(w, 0)
+    total = float(cum[-1])
+    cuts = [0]
+    for r in range(1, world_size):
+        cuts.append(int(torch.searchsorted(cum, torch.tensor(total * r / world_size, dtype=cum.dtype,
+                                                             device=cum.device)).item()) + 1)
+    cuts.append(h)
+    for r in range(1, world_size + 1):                     # keep the bands non-empty and ordered
+        cuts[r] = max(cuts[r], cuts[r - 1] + 1) if r < world_size else h
+    return cuts[rank], cuts[rank + 1]
+
+
 def allreduce_accumulators(images, group=None):
     """Sum the aggregation accumulators over ranks (border overlap + band union)."""
     dist.all_reduce(images.deno, op=dist.ReduceOp.SUM, group=group)
@@ -77,16 +96,25 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
             stats.setdefault("allreduce_events", []).append((e0, e1))
 
         basic = None
+        row_hist = None
+        st = stats if stats is not None else {}
         for step in (0, 1):
             images = alloc.allocate_images(noisy, basic, clean)
             args = get_args(params, c, step, device)
-            y_range = partition_rows_snake(h, args.ps, world, rank) if balance else partition_rows(h, args.ps, world, rank)
-            if schedule == "fast":
-                step_fn(images, dflows, args, stats, y_range, reduce_fn)
+            if not balance:
+                y_range = partition_rows(h, args.ps, world, rank)
+            elif step == 1 and row_hist is not None:
+                y_range = partition_rows_weighted(row_hist, args.ps, world, rank)     # balanced on step-1 group density
             else:
-                step_fn(images, dflows, args, stats, y_range, reduce_fn)
+                y_range = partition_rows_snake(h, args.ps, world, rank)
+            st["want_row_hist"] = bool(balance and step == 0 and schedule == "fast")
+            step_fn(images, dflows, args, st, y_range, reduce_fn)
             if step == 0:
                 basic = images["deno"].clone()
+                if st.get("row_hist") is not None:
+                    row_hist = st.pop("row_hist")
+                    dist.all_reduce(row_hist, op=dist.ReduceOp.SUM, group=group)
+        st.pop("want_row_hist", None)
         deno = images["deno"]
         torch.cuda.synchronize(device)
         if stats is not None and "allreduce_events" in stats:

@@ -47,6 +47,9 @@ class _Workspace:
             ws.vals, ws.inds, ws.qinds = ws.vals2[0], ws.inds2[0], ws.qinds2[0]
             ws.counters4 = torch.zeros((4, 2), dtype=torch.int32, device=device)
             ws.host4 = torch.zeros((4, 2), dtype=torch.int32).pin_memory()
+            ws.ev_search = [torch.cuda.Event() for _ in range(2)]     # re-used every round (no per-round garbage)
+            ws.ev_bayes = [torch.cuda.Event() for _ in range(2)]
+            ws.ev_copied = [torch.cuda.Event() for _ in range(4)]
             ws.search_stream = torch.cuda.Stream(device=device)
             ws.bayes_stream = torch.cuda.Stream(device=device)
             ws.counters = torch.zeros((2,), dtype=torch.int32, device=device)
@@ -116,7 +119,7 @@ def _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap,
     return nproc, nrounds, nmask0
 
 
-def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed, est_mask):
+def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed, est_mask, row_hist=None):
     """Like _rounds_overlapped, but the host never waits for the GPU inside the loop: every kernel of a
     round is enqueued with `cap` rows (rows beyond the number actually drawn are padded to invalid queries
     and skipped on the device), the round size is read back two rounds late from a ring of pinned counters,
@@ -127,7 +130,8 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
     sA, sB = ws.search_stream, ws.bayes_stream
     sA.wait_stream(main)
     sB.wait_stream(main)
-    done_search, done_bayes, copied = [None, None], [None, None], [None] * 4
+    done_search, done_bayes, copied = ws.ev_search, ws.ev_bayes, ws.ev_copied
+    used_bayes = [False, False]
     nproc, nrounds, nmask0 = 0, 0, None
     remaining = int(est_mask)            # until the first read-back: analytic size of the lattice
     qmin = min(qmin, max(296, remaining // 64))
@@ -141,22 +145,23 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
             st = L.stream_ptr()
             cnt = ws.counters4[slot]
             cnt.zero_()
-            if done_bayes[buf] is not None:
+            if used_bayes[buf]:
                 sA.wait_event(done_bayes[buf])                               # round r-2 is done with this buffer
             qinds, vals, inds = ws.qinds2[buf], ws.vals2[buf], ws.inds2[buf]
             L.check(L.lib.vnlb_count_mask(L.ptr(mask), t, h, w, L.ptr(cnt), st), "vnlb_count_mask")
             L.check(L.lib.vnlb_select_queries(L.ptr(mask), t, h, w, prob, seed, r, L.ptr(qinds), cap, L.ptr(cnt), st),
                     "vnlb_select_queries")
             L.check(L.lib.vnlb_pad_queries(L.ptr(qinds), L.ptr(cnt), cap, st), "vnlb_pad_queries")
+            if row_hist is not None:     # groups per image row (multi-GPU: balances the bands of the next step)
+                yq = qinds[:, 1]
+                row_hist.index_add_(0, yq.clamp(min=0), (yq >= 0).to(row_hist.dtype))
             ws.host4[slot].copy_(cnt, non_blocking=True)
-            copied[slot] = torch.cuda.Event()
             copied[slot].record(sA)
             tok = tm.start("search_s%d" % args.step) if tm else None
             search.exec_sim_search_burst(srch_img, qinds, vals, inds, flows, args.sigma, args)
             if tm:
                 tm.stop(tok)
             search_mask.update_mask_inds(mask, inds, c, boost=args.aggreBoost)
-            done_search[buf] = torch.cuda.Event()
             done_search[buf].record(sA)
         with torch.cuda.stream(sB):
             sB.wait_event(done_search[buf])
@@ -164,8 +169,8 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
             deno.bayes_aggregate_fused(images, inds, args)
             if tm:
                 tm.stop(tok)
-            done_bayes[buf] = torch.cuda.Event()
             done_bayes[buf].record(sB)
+            used_bayes[buf] = True
         r += 1
         if r >= 2:                       # read back round r-2 (long finished: no stall in steady state)
             old = (r - 2) & 3
@@ -211,8 +216,12 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
             bands = [(0, h)] if y_range is None else ([y_range] if isinstance(y_range[0], int) else list(y_range))
             rows = sum(min(b, h - args.ps + 1) - a for a, b in bands)
             est = (t - args.pt + 1) * max(rows, 1) * (w - args.ps + 1) // (args.procStep ** 2)
+            row_hist = None
+            if stats is not None and stats.get("want_row_hist"):
+                row_hist = torch.zeros((h,), dtype=torch.float32, device=dev)
+                stats["row_hist"] = row_hist
             nproc, nrounds, nmask0 = _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed,
-                                                   est + est // 8)
+                                                   est + est // 8, row_hist)
         else:
             nproc, nrounds, nmask0 = _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed)
         finish_step(images, args, reduce_fn)
