@@ -513,3 +513,60 @@ def test_refinement_matches_oracle(vb):
     search.exec_refinement(None, bufs, 20.)
     np.testing.assert_array_equal(bufs.inds.cpu().numpy(), ref)
     assert (ref[3] == -1).all() and (ref != -1).any()
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE configs 2 and 3)
+def test_full_size_properties_854x480x20(vb):
+    """At the size the metric is quoted on (oracle far too slow there): size-independent properties."""
+    from vnlb_b200 import color, deno, mask as gm, search
+    from vnlb_b200.utils import AttrDict
+    from vnlb_b200 import synth
+    T, H, W, sigma = 20, 480, 854, 20.
+    clean = synth.synth_video(T, H, W)
+    noisy = synth.add_noise(clean, sigma)
+    yuv = color.rgb2yuv(cu(noisy))
+    # --- search on 4096 lattice pixels spread over the video ---
+    a = gargs(vb, 0)
+    m, nset = gm.init_mask(yuv.shape, a, DEV)
+    assert 0.10 < nset / (T * H * W) < 0.13                          # stride-3 lattice: ~1/9 of the pixels
+    q = torch.nonzero(m)[:: nset // 4096][:4096].contiguous()
+    k = a.npatches
+    vals = torch.empty((q.shape[0], k), device=DEV)
+    inds = torch.empty((q.shape[0], k), dtype=torch.int64, device=DEV)
+    search.exec_sim_search_burst(yuv, q, vals, inds, None, sigma, a)
+    v, i, qq = vals.cpu().numpy(), inds.cpu().numpy(), q.cpu().numpy()
+    chw, hw = 3 * H * W, H * W
+    self_ind = qq[:, 0] * chw + qq[:, 1] * W + qq[:, 2]
+    assert np.array_equal(i[:, 0], self_ind) and np.all(v[:, 0] == 0)          # self match first, distance 0
+    assert np.all(np.diff(v, axis=1) >= 0) and np.all(i >= 0)                 # ascending, all valid
+    t, y, x = i // chw, (i % hw) // W, i % W
+    assert np.all(np.abs(t - qq[:, [0]]) <= 12) and np.all(t <= T - 2)         # inside the (shifted) temporal window
+    assert np.all(np.abs(y - qq[:, [1]]) <= 26) and np.all(np.abs(x - qq[:, [2]]) <= 26)
+    assert np.all(y <= H - 7) and np.all(x <= W - 7)
+    assert all(len(set(r)) == k for r in i[:256])                             # no candidate twice
+    # spot check 8 queries against the oracle bit for bit
+    sel = np.linspace(0, qq.shape[0] - 1, 8).astype(int)
+    ov = np.full((8, k), np.inf, np.float32)
+    oi = np.full((8, k), -1, np.int64)
+    orc.exec_sim_search_burst(yuv.cpu().numpy(), qq[sel], ov, oi, None, sigma, oargs(0))
+    assert np.array_equal(oi, i[sel]) and np.array_equal(ov, v[sel])
+    # --- fused filter + aggregation: weight checksum and a partition of unity after normalisation ---
+    images = AttrDict(noisy=yuv, basic=yuv, deno=torch.zeros_like(yuv), weights=torch.zeros((T, H, W), device=DEV))
+    deno.bayes_aggregate_fused(images, inds, a)
+    assert float(images.weights.sum().item()) == q.shape[0] * k * 98          # every patch pixel counted once
+    wts = images.weights
+    est = images.deno[:, 0][wts > 0] / wts[wts > 0]
+    ref = yuv[:, 0][wts > 0]
+    assert float((est - ref).abs().mean()) < 0.8 * sigma * 3 ** 0.5            # estimate is closer than the noise (Y has std sigma)
+    assert torch.isfinite(images.deno).all()
+
+
+def test_constant_video_is_a_fixed_point(vb):
+    """Idempotence-type property: a noise-free constant video has zero covariance everywhere (m = 0),
+    exact-tie searches, and must come back unchanged from both steps."""
+    vid = np.full((4, 3, 40, 44), 100.0, np.float32)
+    vid[:, 1] = 50.0
+    for sched in ("parity", "fast"):
+        torch.manual_seed(0)
+        deno, basic, _ = vb.denoise(vid, 20., schedule=sched, verbose=False)
+        assert np.abs(basic.cpu().numpy() - vid).max() < 1e-3 and np.abs(deno.cpu().numpy() - vid).max() < 1e-3
