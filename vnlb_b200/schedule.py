@@ -34,7 +34,8 @@ class _Workspace:
         key = (str(device), cap, k, pt, c, ps, stacks)
         ws = cls._cache.get(key)
         if ws is None:
-            cls._cache.clear()
+            if len(cls._cache) >= 4:          # both steps (k = 100 / 60) keep their buffers between calls
+                cls._cache.clear()
             ws = AttrDict()
             rows = cap if stacks else 0     # the fused kernel never materialises the patch stacks
             ws.noisy = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
