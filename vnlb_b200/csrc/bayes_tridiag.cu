@@ -28,6 +28,10 @@
 //     noisy/basic images through `inds`, decides the flat flag, filters all channels and
 //     scatters the result into the aggregation accumulators with float atomics -- the
 //     patch stacks, vpss.fill_patches, exec_flat_areas and agg_patches never touch HBM.
+#include <stdlib.h>
+
+#include <mutex>
+
 #include "common.cuh"
 
 namespace vnlb {
@@ -125,10 +129,18 @@ struct BayesArgs {
     // common
     const long long *inds;
     float *rank_var;
+    float *ws;                     // split path: per-problem workspace (see cov_tridiag_kernel)
+    int ws_stride;                 // floats per problem
     VnlbBayesParams P;
     TriLayout L;
 };
 
+// named barrier over the first `nthr` threads' warps (a multiple of 32); barrier 0 is __syncthreads
+__device__ __forceinline__ void bar_sync_n(int id, int nthr) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthr) : "memory"); }
+// Warp w of every CTA runs on sub-partition w % 4 of its SM, and in several phases the low warps carry most of
+// the work (rows retire from the top in the tridiagonalisation, one thread per eigenpair in the twisted
+// factorisation).  Rotating the warp numbering by a per-CTA hash spreads that load over the 4 schedulers.
+__device__ __forceinline__ int warp_rotation() { return (int)((blockIdx.x * 0x9E3779B1u) >> 30); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -253,7 +265,310 @@ __device__ __forceinline__ void gram_map(float *Vt, const float *Ut, const float
     }
 }
 
-template <bool FUSED, bool GRAM>
+
+// ---------------------------------------------------------------------------------------------
+// Split path, first kernel: centre + covariance + Householder tridiagonalisation with the matrix held
+// in REGISTERS (QD = compile-time dimension of the eigenproblem; thread t < QD owns one full row).
+// One CTA of 128 threads per (group, channel) problem; 168 registers => 3 CTAs per SM, which is why
+// this stage is its own kernel: the latency-bound phases 2-5 keep their 5 CTAs per SM in bayes_kernel.
+// Output per problem in the workspace (floats): d[LDQ] e[LDQ] tau[LDQ] mean[LDQ] reflectors[nref],
+// the reflectors packed exactly like the shared-memory path packs them.
+//
+// The rows are held index-reversed, b_t[j] = A[QD-1-t][QD-1-j], and columns are eliminated from the
+// last one down, which is the forward elimination of A (same d, e, tau and reflectors as the
+// shared-memory path up to rounding): the trailing matrix shrinks towards thread 0 / register 0, so
+// whole warps retire (QD = 98: 2.06 warps active on average) and the unrolled column loops are entered
+// through a fall-through switch at the first live block of 16 columns.
+//
+// Step for column c (trailing size c; x = column c, r = column c-1 of the trailing matrix, both in shared memory,
+// element j written by the thread that owns row j):
+//   y       = B x~               (x~ = x[0..c-1]; thread c takes part: y_c = |x~|^2 = alpha^2 + ssq)
+//   beta    = -sign(alpha) sqrt(y_c), tau = (beta - alpha)/beta, v = (x~ - beta e_{c-1}) / (alpha - beta)
+//   B v     = (y - beta r) / (alpha - beta)                     -- no second pass over the matrix
+//   v^T B v = (x~^T y - 2 beta y_{c-1} + beta^2 r_{c-1}) / (alpha - beta)^2   -- one block reduction
+//   w       = tau B v - (tau^2 v^T B v / 2) v ;   B <- B - v w^T - w v^T
+// After the reduction every thread also knows w_{c-1} and w_{c-2} (from y_{c-1}, y_{c-2}), so thread j forms ITS
+// elements of the next step's x and r (columns c-1 and c-2 after the update) before the update and publishes them
+// together with v_j and w_j: TWO barriers per step and 5 scalar STS per thread (a barrier drains the pending
+// shared-memory stores).  The update of step c and the matvec of step c-1 are ONE sweep over the registers: per
+// 4 columns 3 broadcast LDS.128 (v, w, next x) + 6 FFMA2.  Column c-2 of a row is a dynamically indexed register:
+// a 4-column window copy of the registers (re-read every 4th step through a switch, updated like the registers
+// in between) provides it with a 4-way select.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    uint32_t a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+    return a;
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_newton(float x) {   // 1/x: MUFU.RCP + one Newton step, no special cases
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * fmaf(-x, r, 2.f);
+}
+
+// Shared scratch of tridiag_regs (floats): 2 x {xs, rs} ping-pong, vs, ws, 2 x 12 scalars, d, e, tau, packed reflectors.
+template <int QD> __host__ __device__ constexpr int tridiag_scratch_floats() {
+    return 6 * (((QD + 3) & ~3) + 4) + 24 + 3 * ((QD + 3) & ~3) + ((((QD - 1) * QD / 2) + 3) & ~3);
+}
+
+template <int QD>
+__device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((QD + 3) / 4)], float *sv, float *out, int tid) {
+    constexpr int LDQ = (QD + 3) & ~3;
+    constexpr int NCH = LDQ / 4;
+    constexpr int NB2 = (NCH + 1) / 2;             // blocks of 2 chunks = 8 columns
+    constexpr int VL = LDQ + 4;
+    constexpr int NREF = (((QD - 1) * QD / 2) + 3) & ~3;
+    static_assert(NB2 <= 13 && QD >= 8, "tridiag_regs: 8 <= QD <= 104");
+    const uint32_t s0 = smem_u32(sv);
+    const uint32_t aV = s0 + 16 * VL, aW = s0 + 20 * VL, aRed = s0 + 24 * VL;   // byte addresses
+    const uint32_t aD = aRed + 96, aE = aD + 4 * LDQ, aTau = aE + 4 * LDQ, aRefl = aTau + 4 * LDQ;
+    const int lane = tid & 31, warp = tid >> 5;     // logical (rotated) warp: see warp_rotation()
+    for (int j = tid; j < 6 * VL + 24; j += TT) sv[j] = 0.f;
+    __syncthreads();
+    constexpr int c0 = QD - 1;
+    float xi, ri, yi = 0.f;
+    {   // columns QD-1 and QD-2 of the untouched matrix
+        const float x0 = (c0 & 1) ? b[c0 >> 1].y : b[c0 >> 1].x;
+        const float r0 = ((c0 - 1) & 1) ? b[(c0 - 1) >> 1].y : b[(c0 - 1) >> 1].x;
+        if (tid < c0) { sts32(s0 + 4 * tid, x0); sts32(s0 + 4 * (VL + tid), r0); }
+        if (tid == c0) sts32(aRed + 24, x0);
+        xi = tid < c0 ? x0 : 0.f;
+        ri = r0;
+    }
+    int Iw = (c0 - 2) >> 2;                        // the window holds columns 4 Iw .. 4 Iw + 3 of this row
+    float win0 = b[2 * ((c0 - 2) >> 2)].x, win1 = b[2 * ((c0 - 2) >> 2)].y, win2 = b[2 * ((c0 - 2) >> 2) + 1].x, win3 = b[2 * ((c0 - 2) >> 2) + 1].y;
+    __syncthreads();
+    if (tid <= c0) {                               // y = B x for the first column
+        float2 y0 = make_float2(0.f, 0.f), y1 = y0, y2 = y0, y3 = y0;
+#pragma unroll
+        for (int I = 0; I < NCH; ++I) {
+            const float4 x4 = lds128(s0 + 16 * I);
+            if (I & 1) { y2 = __ffma2_rn(b[2 * I], make_float2(x4.x, x4.y), y2); y3 = __ffma2_rn(b[2 * I + 1], make_float2(x4.z, x4.w), y3); }
+            else       { y0 = __ffma2_rn(b[2 * I], make_float2(x4.x, x4.y), y0); y1 = __ffma2_rn(b[2 * I + 1], make_float2(x4.z, x4.w), y1); }
+        }
+        yi = ((y0.x + y0.y) + (y1.x + y1.y)) + ((y2.x + y2.y) + (y3.x + y3.y));
+    }
+    for (int c = QD - 1; c >= 2; --c) {
+        if (32 * warp > c) break;                  // this warp's rows are all eliminated: it leaves (named barriers below)
+        const int k = QD - 1 - c;
+        const int nb2 = (c + 7) >> 3;              // live 8-column blocks
+        const int nthr = 32 * ((c >> 5) + 1);      // threads of the warps still in the loop
+        const uint32_t pp = k & 1;
+        const uint32_t aX = s0 + pp * (8 * VL), aR = aX + 4 * VL, aXn = s0 + (pp ^ 1) * (8 * VL), aRn = aXn + 4 * VL;
+        const uint32_t aRd = aRed + pp * 48, aRdn = aRed + (pp ^ 1) * 48;
+        const bool active = tid < c;
+        const float part = warp_sum(xi * yi);      // xi = 0 for tid >= c
+        if (lane == 0) sts32(aRd + 4 * warp, part);
+        if (tid == c) sts32(aRd + 16, yi);
+        if (tid == c - 1) sts32(aRd + 20, yi);
+        if (tid == c - 2) sts32(aRd + 36, yi);
+        bar_sync_n(1, nthr);                                                          // B1
+        const float4 r0 = lds128(aRd), r1 = lds128(aRd + 16);
+        const float ycm2 = lds32(aRd + 36);
+        const float alpha = lds32(aX + 4 * (c - 1)), bcc = lds32(aR + 4 * (c - 1));
+        const float xcm2 = lds32(aX + 4 * (c - 2)), rcm2 = lds32(aR + 4 * (c - 2));
+        float xBx = r0.x;                          // partial sums of the warps still in the loop, in warp order
+        if (nthr > 32) xBx += r0.y;
+        if (nthr > 64) xBx += r0.z;
+        if (nthr > 96) xBx += r0.w;
+        // y_c and alpha^2 come from two roundings of the same entries: clamp, so that a trailing block at rounding-noise
+        // level takes the skip path instead of the square root of a negative number
+        const float a2 = alpha * alpha;
+        const float nrm2 = fmaxf(r1.x, a2), ycm1 = r1.y, dk = r1.z;
+        const bool skip = (nrm2 == a2);            // nothing to annihilate: H = I (tau = 0, v = e_{c-1}, w = 0)
+        const float rsq = rsqrt_approx(nrm2);
+        float sq = nrm2 * rsq;
+        sq = fmaf(0.5f * rsq, fmaf(-sq, sq, nrm2), sq);                                // sqrt(nrm2), one Newton step
+        const float beta = skip ? alpha : -copysignf(sq, alpha);   // skip: keeps every product below finite (and e_k = alpha)
+        const float tau = skip ? 0.f : (beta - alpha) * rcp_newton(beta);
+        const float scale = skip ? 0.f : rcp_newton(alpha - beta);
+        const float ts = tau * scale;
+        const float uBu = fmaf(beta * beta, bcc, fmaf(-2.f * beta, ycm1, xBx));
+        const float hs = 0.5f * ts * ts * uBu;     // tau * (v^T p) / 2
+        const float vi = (tid == c - 1) ? 1.f : xi * scale;
+        const float wi = fmaf(-hs, vi, ts * fmaf(-beta, ri, yi));
+        const float wcm1 = fmaf(-hs, 1.f, ts * fmaf(-beta, bcc, ycm1));               // w_{c-1}  (v_{c-1} = 1)
+        const float vcm2 = xcm2 * scale;
+        const float wcm2 = fmaf(-hs, vcm2, ts * fmaf(-beta, rcm2, ycm2));             // w_{c-2}
+        const int wsel = (c - 2) & 3;
+        const float qi = wsel == 0 ? win0 : (wsel == 1 ? win1 : (wsel == 2 ? win2 : win3));   // b[c-2] of this row
+        // this row's elements of columns c-1 and c-2 after the update, in the update's own operation order
+        const float xnext = fmaf(-vi, wcm1, fmaf(-wi, 1.f, ri));
+        const float rnext = fmaf(-vi, wcm2, fmaf(-wi, vcm2, qi));
+        if (active) {
+            sts32(aV + 4 * tid, vi);
+            sts32(aW + 4 * tid, wi);
+            sts32(aRefl + 4 * (k * (QD - 1) - (k * (k - 1)) / 2 + (c - 1 - tid)), vi);
+            sts32(aXn + 4 * tid, (tid < c - 1) ? xnext : 0.f);
+            sts32(aRn + 4 * tid, rnext);
+            if (tid == c - 1) sts32(aRdn + 24, xnext);    // B[c-1][c-1]: the next diagonal entry
+        }
+        if (tid == c) sts32(aXn + 4 * tid, 0.f);
+        if (tid == 0) { sts32(aD + 4 * k, dk); sts32(aE + 4 * k, beta); sts32(aTau + 4 * k, tau); }
+        bar_sync_n(1, nthr);                                                          // B2
+        yi = 0.f;
+        if (active) {
+            const float2 nvi = make_float2(-vi, -vi), nwi = make_float2(-wi, -wi);
+            float2 y0 = make_float2(0.f, 0.f), y1 = y0, y2 = y0, y3 = y0;
+#define VNLB_SW1(J)                                                                      \
+            if constexpr ((J) < NCH) {                                                  \
+                constexpr int I = (J) < NCH ? (J) : 0;                                  \
+                const float4 v4 = lds128(aV + 16 * I), w4 = lds128(aW + 16 * I), x4 = lds128(aXn + 16 * I);                       \
+                b[2 * I] = __ffma2_rn(nvi, make_float2(w4.x, w4.y), __ffma2_rn(nwi, make_float2(v4.x, v4.y), b[2 * I]));         \
+                b[2 * I + 1] = __ffma2_rn(nvi, make_float2(w4.z, w4.w), __ffma2_rn(nwi, make_float2(v4.z, v4.w), b[2 * I + 1])); \
+                if (I & 1) { y2 = __ffma2_rn(b[2 * I], make_float2(x4.x, x4.y), y2); y3 = __ffma2_rn(b[2 * I + 1], make_float2(x4.z, x4.w), y3); } \
+                else       { y0 = __ffma2_rn(b[2 * I], make_float2(x4.x, x4.y), y0); y1 = __ffma2_rn(b[2 * I + 1], make_float2(x4.z, x4.w), y1); } \
+            }
+#define VNLB_SWB(G) case (G) + 1: { VNLB_SW1(2 * (G) + 1) VNLB_SW1(2 * (G)) }
+            switch (nb2) {
+                VNLB_SWB(12) VNLB_SWB(11) VNLB_SWB(10) VNLB_SWB(9) VNLB_SWB(8) VNLB_SWB(7) VNLB_SWB(6)
+                VNLB_SWB(5) VNLB_SWB(4) VNLB_SWB(3) VNLB_SWB(2) VNLB_SWB(1) VNLB_SWB(0)
+                default: break;
+            }
+#undef VNLB_SWB
+#undef VNLB_SW1
+            yi = ((y0.x + y0.y) + (y1.x + y1.y)) + ((y2.x + y2.y) + (y3.x + y3.y));
+            {   // the window copy gets the same update
+                const float4 v4 = lds128(aV + 16 * Iw), w4 = lds128(aW + 16 * Iw);
+                win0 = fmaf(-vi, w4.x, fmaf(-wi, v4.x, win0)); win1 = fmaf(-vi, w4.y, fmaf(-wi, v4.y, win1));
+                win2 = fmaf(-vi, w4.z, fmaf(-wi, v4.z, win2)); win3 = fmaf(-vi, w4.w, fmaf(-wi, v4.w, win3));
+            }
+        }
+        if (c >= 3 && ((c - 3) >> 2) != Iw) {      // next step needs column c-3: re-read the window from the registers
+            Iw = (c - 3) >> 2;
+            switch (Iw) {
+#define VNLB_W(J) case (J): if constexpr ((J) < NCH) { win0 = b[2 * ((J) < NCH ? (J) : 0)].x; win1 = b[2 * ((J) < NCH ? (J) : 0)].y; win2 = b[2 * ((J) < NCH ? (J) : 0) + 1].x; win3 = b[2 * ((J) < NCH ? (J) : 0) + 1].y; } break;
+                VNLB_W(0) VNLB_W(1) VNLB_W(2) VNLB_W(3) VNLB_W(4) VNLB_W(5) VNLB_W(6) VNLB_W(7) VNLB_W(8) VNLB_W(9) VNLB_W(10) VNLB_W(11) VNLB_W(12)
+                VNLB_W(13) VNLB_W(14) VNLB_W(15) VNLB_W(16) VNLB_W(17) VNLB_W(18) VNLB_W(19) VNLB_W(20) VNLB_W(21) VNLB_W(22) VNLB_W(23) VNLB_W(24) VNLB_W(25)
+#undef VNLB_W
+                default: break;
+            }
+        }
+        xi = (tid < c - 1) ? xnext : 0.f;
+        ri = rnext;
+    }
+    // the last 2 x 2 block: B[1][1], B[1][0], B[0][0]
+    if (tid == 1) { sts32(aD + 4 * (QD - 2), b[0].y); sts32(aE + 4 * (QD - 2), b[0].x); sts32(aTau + 4 * (QD - 2), 0.f); }
+    if (tid == 0) { sts32(aD + 4 * (QD - 1), b[0].x); sts32(aE + 4 * (QD - 1), 0.f); sts32(aTau + 4 * (QD - 1), 0.f); }
+    __syncthreads();
+    // flush (d, e, tau | reflectors) to the workspace, coalesced
+    float4 *o4 = reinterpret_cast<float4 *>(out);
+    const float *sd = sv + 6 * VL + 24;
+    for (int idx = threadIdx.x; idx < 3 * (LDQ / 4); idx += TT) o4[idx] = reinterpret_cast<const float4 *>(sd)[idx];
+    for (int idx = threadIdx.x; idx < NREF / 4; idx += TT) o4[LDQ + idx] = reinterpret_cast<const float4 *>(sd + 3 * LDQ)[idx];
+}
+
+template <int QD> constexpr int split_ws_stride() { return 4 * ((QD + 3) & ~3) + ((((QD - 1) * QD / 2) + 3) & ~3); }
+
+template <bool FUSED, int QD>
+__global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
+    constexpr int LDQ = (QD + 3) & ~3, NCH = LDQ / 4;
+    extern __shared__ __align__(16) float sm[];
+    const VnlbBayesParams &P = a.P;
+    const int n = P.k, ps = P.ps, ps2 = ps * ps, C = P.c;
+    const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + warp_rotation()) & (TT / 32 - 1), tid = 32 * warp + lane;
+    const int g = blockIdx.x / C, ch = blockIdx.x - g * C;
+    if (a.inds && !row_valid_block(a.inds + (long long)g * n, n)) return;
+    float *Y = sm;                                   // Y[n][LDQ]: patches, columns reversed (column j = patch element QD-1-j)
+    const int ybody = max(n * LDQ, tridiag_scratch_floats<QD>());
+    int *pb = (int *)(sm + ybody);                   // fused: offset of the patch corner in the image
+    float *sv = sm;                                  // the tridiagonalisation's vectors re-use the head of Y
+    const int rstride = P.pt * C * ps2;
+    const long long HW = (long long)a.H * a.W, CHW = HW * C;
+    if (FUSED) {
+        int bad = 0;
+        for (int nn = tid; nn < n; nn += TT) {
+            int t, y, x;
+            decode_ind(a.inds[(long long)g * n + nn], a.H, a.W, C, t, y, x);
+            bad |= (t < 0 || t + P.pt > a.T || y + ps > a.H || x + ps > a.W);
+            pb[nn] = (int)((long long)t * CHW + (long long)y * a.W + x);
+        }
+        if (__syncthreads_or(bad)) return;           // malformed index: the group is skipped (bayes_kernel does the same)
+    }
+    auto col_off = [&](int j) -> int {
+        const int dt = j / ps2, r = j - dt * ps2;
+        if (FUSED) { const int dy = r / ps, dx = r - dy * ps; return (int)(dt * CHW + ch * HW + (long long)dy * a.W + dx); }
+        return (dt * C + ch) * ps2 + r;
+    };
+    const float *src = FUSED ? (P.cov_from_basic ? a.img_basic : a.img_noisy)
+                             : (P.cov_from_basic ? a.pbasic : a.pnoisy) + (long long)g * n * rstride;
+    int co[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) co[q] = col_off(min(lane + 32 * q, QD - 1));
+    // ---- stage all n patches (every load independent: one exposed latency)
+    for (int nn = warp; nn < n; nn += TT / 32) {
+        const float *q = src + (FUSED ? (long long)pb[nn] : (long long)nn * rstride);
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+            const int j = lane + 32 * qq;
+            if (j < QD) Y[nn * LDQ + (QD - 1 - j)] = q[co[qq]];
+            else if (j < LDQ) Y[nn * LDQ + j] = 0.f;                                 // zero pad columns QD..LDQ-1
+        }
+    }
+    __syncthreads();
+    // ---- centre (same summation order as bayes_kernel: 4 interleaved partial sums)
+    const float inv_n = 1.f / (float)n;
+    float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
+    if (tid < LDQ) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int nn = 0;
+        for (; nn + 3 < n; nn += 4) {
+            s0 += Y[nn * LDQ + tid]; s1 += Y[(nn + 1) * LDQ + tid];
+            s2 += Y[(nn + 2) * LDQ + tid]; s3 += Y[(nn + 3) * LDQ + tid];
+        }
+        for (; nn < n; ++nn) s0 += Y[nn * LDQ + tid];
+        const float mj = ((s0 + s1) + (s2 + s3)) * inv_n;
+        for (nn = 0; nn < n; ++nn) Y[nn * LDQ + tid] -= mj;
+        if (tid < QD) wsp[3 * LDQ + (QD - 1 - tid)] = mj; else wsp[3 * LDQ + tid] = 0.f;
+    }
+    __syncthreads();
+    // ---- covariance, row t of B = C reversed, accumulated over the patches in order (bit-identical to bayes_kernel)
+    float2 b[2 * NCH];
+#pragma unroll
+    for (int j = 0; j < 2 * NCH; ++j) b[j] = make_float2(0.f, 0.f);
+    float dg = 0.f;
+    {
+        const int tcol = min(tid, LDQ - 1);
+        const float live = tid < QD ? 1.f : 0.f;
+        for (int nn = 0; nn < n; ++nn) {
+            const float *row = Y + nn * LDQ;
+            const float own = row[tcol] * live;
+            const float2 od = make_float2(own, own);
+            dg = fmaf(own, own, dg);
+#pragma unroll
+            for (int jj = 0; jj < NCH; ++jj) {
+                const float4 f = *reinterpret_cast<const float4 *>(row + 4 * jj);
+                b[2 * jj] = __ffma2_rn(od, make_float2(f.x, f.y), b[2 * jj]);
+                b[2 * jj + 1] = __ffma2_rn(od, make_float2(f.z, f.w), b[2 * jj + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2 * NCH; ++j) { b[j].x *= inv_n; b[j].y *= inv_n; }
+    __syncthreads();                                 // Y is dead
+    if (a.rank_var) {                                // rank_var = mean over channels of trace(C) (bayes_est.py:39-40)
+        float tr = warp_sum(dg * inv_n);
+        float *red = sm + ybody + ((n + 3) & ~3);
+        if (lane == 0) red[warp] = tr;
+        __syncthreads();
+        if (tid == 0) atomicAdd(&a.rank_var[g], ((red[0] + red[1]) + (red[2] + red[3])) / (float)C);
+    }
+    tridiag_regs<QD>(b, sv, wsp, tid);
+}
+
+// SPLIT: phases 0-1 were done by cov_tridiag_kernel; (d, e, tau, mean, packed reflectors) come from the workspace.
+template <bool FUSED, bool GRAM, bool SPLIT>
 __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs a) {
     constexpr int NT = GRAM ? 1 : 3;               // 4x4 tiles of the (covariance | Gram) matrix per thread
     extern __shared__ __align__(16) float sm[];
@@ -261,7 +576,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
     const TriLayout &L = a.L;
     const int n = P.k, ps = P.ps, ps2 = ps * ps, p = L.p, LD = L.LD, XS = L.XS, C = P.c;
     const int qd = L.q, LDq = L.LDq, ZSq = L.ZSq;   // eigenproblem dimension (p, or n with the Gram trick)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + warp_rotation()) & (TT / 32 - 1), tid = 32 * warp + lane;
     const int g = FUSED ? blockIdx.x : blockIdx.x / C;
     if (a.inds && !row_valid_block(a.inds + (long long)g * n, n)) return;
 
@@ -329,6 +644,20 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
         const float *src = P.cov_from_basic ? base_basic : base_noisy;
         __syncthreads();
 
+        if constexpr (SPLIT) {
+            // (d, e, tau, mean | packed reflectors) of problem (g, ch), written by cov_tridiag_kernel
+            const float4 *wsp = reinterpret_cast<const float4 *>(a.ws + (size_t)(g * C + ch) * a.ws_stride);
+            const int nhead = LDq;                      // 4 vectors of LDq floats = LDq float4
+            for (int idx = tid; idx < nhead; idx += TT) {
+                const float4 f = wsp[idx];
+                const int which = idx / (LDq >> 2), off = 4 * (idx - which * (LDq >> 2));
+                float *dst = which == 0 ? d : (which == 1 ? e : (which == 2 ? taus : mean));
+                *reinterpret_cast<float4 *>(dst + off) = f;
+            }
+            const int nref4 = (((qd - 1) * qd / 2 + 3) & ~3) >> 2;
+            for (int idx = tid; idx < nref4; idx += TT) reinterpret_cast<float4 *>(R)[idx] = wsp[nhead + idx];
+            __syncthreads();
+        } else {
         // -------------------------------------------------------------- 0. centre + covariance
         for (int j = tid; j < LD; j += TT) {
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -539,6 +868,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
             e[qd - 1] = 0.f;
         }
         __syncthreads();
+        }  // !SPLIT
 
         // -------------------------------------------------------------- 2. eigenvalues above the threshold
         // e2[i] = e[i-1]^2 is the coupling that enters pivot i of the Sturm sequence
@@ -824,6 +1154,75 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
     }
 }
 
+// Split path (cov_tridiag_kernel + bayes_kernel<.., SPLIT>) for the production shape of step 1 (7x7x2 patches: q = 98,
+// direct covariance); VNLB_BAYES_SPLIT=0 forces the single-kernel shared-memory path.
+static bool use_split(const TriLayout &L) {
+    static int v = -1;
+    if (v < 0) { const char *s = getenv("VNLB_BAYES_SPLIT"); v = (s && s[0] == '0') ? 0 : 1; }
+    return v != 0 && !L.gram && L.q == 98 && (size_t)(L.n * 100 + L.n + 16) * sizeof(float) <= 72 * 1024;
+}
+
+// Workspace of the split path: one grow-only buffer per (device, stream), so that the two kernels of a call and
+// the calls of one stream re-use it in stream order without allocator traffic (1 GB for 16384 groups x 3 channels).
+static float *split_workspace(size_t bytes, cudaStream_t st) {
+    struct Slot { int dev; cudaStream_t st; float *p; size_t bytes; };
+    static Slot slots[16];
+    static int nslots = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Slot *s = nullptr;
+    for (int i = 0; i < nslots; ++i)
+        if (slots[i].dev == dev && slots[i].st == st) s = &slots[i];
+    if (!s) {
+        if (nslots == 16) {   // recycle the oldest slot
+            cudaDeviceSynchronize();
+            cudaFree(slots[0].p);
+            for (int i = 1; i < 16; ++i) slots[i - 1] = slots[i];
+            nslots = 15;
+        }
+        s = &slots[nslots++];
+        *s = Slot{dev, st, nullptr, 0};
+    }
+    if (s->bytes < bytes) {
+        if (s->p) { cudaStreamSynchronize(st); cudaFree(s->p); s->p = nullptr; s->bytes = 0; }
+        const size_t want = bytes + bytes / 8;
+        if (cudaMalloc((void **)&s->p, want) != cudaSuccess) { s->p = nullptr; return nullptr; }
+        s->bytes = want;
+    }
+    return s->p;
+}
+
+template <bool FUSED>
+static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t st) {
+    const VnlbBayesParams *p = &a.P;
+    const size_t smem = (size_t)a.L.total * sizeof(float);
+    cudaError_t e;
+    if (use_split(a.L)) {
+        constexpr int QD = 98;
+        a.ws_stride = split_ws_stride<QD>();
+        const size_t bytes = (size_t)B * p->c * a.ws_stride * sizeof(float);
+        a.ws = split_workspace(bytes, st);
+        if (!a.ws) { set_error("%s: workspace of %zu bytes: %s", what, bytes, cudaGetErrorString(cudaGetLastError())); return VNLB_ERR_CUDA; }
+        const int ybody = a.L.n * 100 > tridiag_scratch_floats<QD>() ? a.L.n * 100 : tridiag_scratch_floats<QD>();
+        const size_t smem1 = (size_t)(ybody + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
+        auto k1 = cov_tridiag_kernel<FUSED, QD>;
+        auto k2 = bayes_kernel<FUSED, false, true>;
+        e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
+        k1<<<B * p->c, TT, smem1, st>>>(a);
+        k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
+        return check_launch(what);
+    }
+    auto kern = a.L.gram ? bayes_kernel<FUSED, true, false> : bayes_kernel<FUSED, false, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
+    kern<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
+    return check_launch(what);
+}
+
 bool bayes_tridiag_supported(const VnlbBayesParams *p) {
     const int pd = p->pt * p->ps * p->ps;
     if (pd < 3 || pd > TT || p->rank > MR || p->k < 1) return false;
@@ -837,12 +1236,7 @@ int launch_bayes_tridiag(float *pnoisy, const float *pbasic, const unsigned char
     a.pnoisy = pnoisy; a.pbasic = pbasic; a.flat = flat; a.inds = inds; a.rank_var = rank_var;
     a.P = *p;
     a.L = tri_layout(p->k, p->pt * p->ps * p->ps);
-    const size_t smem = (size_t)a.L.total * sizeof(float);
-    auto kern = a.L.gram ? bayes_kernel<false, true> : bayes_kernel<false, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("vnlb_bayes_filter: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
-    kern<<<B * p->c, TT, smem, st>>>(a);
-    return check_launch("vnlb_bayes_filter(tridiag)");
+    return launch_bayes_any<false>(a, B, "vnlb_bayes_filter(tridiag)", st);
 }
 
 int launch_bayes_fused(const float *img_noisy, const float *img_basic, const long long *inds, int B, int T, int H,
@@ -853,12 +1247,7 @@ int launch_bayes_fused(const float *img_noisy, const float *img_basic, const lon
     a.T = T; a.H = H; a.W = W; a.flat_thresh = flat_thresh;
     a.P = *p;
     a.L = tri_layout(p->k, p->pt * p->ps * p->ps);
-    const size_t smem = (size_t)a.L.total * sizeof(float);
-    auto kern = a.L.gram ? bayes_kernel<true, true> : bayes_kernel<true, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("vnlb_bayes_aggregate_fused: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
-    kern<<<B, TT, smem, st>>>(a);
-    return check_launch("vnlb_bayes_aggregate_fused");
+    return launch_bayes_any<true>(a, B, "vnlb_bayes_aggregate_fused", st);
 }
 
 }  // namespace vnlb
