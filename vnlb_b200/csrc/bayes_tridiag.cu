@@ -317,24 +317,35 @@ __device__ __forceinline__ float rcp_newton(float x) {   // 1/x: MUFU.RCP + one 
     return r * fmaf(-x, r, 2.f);
 }
 
+// The elimination runs in PHASES, each its own kernel: a phase holds the NR x NR trailing matrix (NR rows = NR threads
+// used, NR columns = NR registers per thread) and eliminates columns NR-1 .. CEND; unless CEND == 2 it then hands
+// the CEND x CEND trailing matrix to the next phase through the workspace.  The register budget (hence the CTAs
+// per SM) follows the trailing size, which is what the latency-bound loop needs.  QDG = dimension of the whole
+// problem: step index k = QDG-1-c and the packed reflector offsets are global.
+__host__ __device__ constexpr int refl_off(int qdg, int k) { return k * (qdg - 1) - (k * (k - 1)) / 2; }
 // Shared scratch of tridiag_regs (floats): 2 x {xs, rs} ping-pong, vs, ws, 2 x 12 scalars, d, e, tau, packed reflectors.
-template <int QD> __host__ __device__ constexpr int tridiag_scratch_floats() {
-    return 6 * (((QD + 3) & ~3) + 4) + 24 + 3 * ((QD + 3) & ~3) + ((((QD - 1) * QD / 2) + 3) & ~3);
+template <int QDG, int NR, int CEND> __host__ __device__ constexpr int tridiag_scratch_floats() {
+    return 6 * (((NR + 3) & ~3) + 4) + 24 + 3 * ((NR - CEND + 5) & ~3) +
+           ((refl_off(QDG, QDG - CEND) - refl_off(QDG, QDG - NR) + 3) & ~3);
 }
 
-template <int QD>
-__device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((QD + 3) / 4)], float *sv, float *out, int tid) {
+template <int QDG, int NR, int CEND, int NT>
+__device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((NR + 3) / 4)], float *sv, float *out, float *trail, int tid) {
+    constexpr int QD = NR;
     constexpr int LDQ = (QD + 3) & ~3;
+    constexpr int LDG = (QDG + 3) & ~3;
     constexpr int NCH = LDQ / 4;
     constexpr int NB2 = (NCH + 1) / 2;             // blocks of 2 chunks = 8 columns
     constexpr int VL = LDQ + 4;
-    constexpr int NREF = (((QD - 1) * QD / 2) + 3) & ~3;
-    static_assert(NB2 <= 13 && QD >= 8, "tridiag_regs: 8 <= QD <= 104");
+    constexpr int K0 = QDG - NR, K1 = QDG - 1 - CEND;          // steps of this phase: k = K0 .. K1
+    constexpr int KN = (K1 - K0 + 1 + 2 + 3) & ~3;             // + the two trailing entries of the last phase
+    constexpr int R0 = refl_off(QDG, K0), R1 = refl_off(QDG, K1 + 1);
+    static_assert(NB2 <= 13 && QD >= 8 && CEND >= 2 && CEND < NR, "tridiag_regs: 8 <= NR <= 104");
     const uint32_t s0 = smem_u32(sv);
     const uint32_t aV = s0 + 16 * VL, aW = s0 + 20 * VL, aRed = s0 + 24 * VL;   // byte addresses
-    const uint32_t aD = aRed + 96, aE = aD + 4 * LDQ, aTau = aE + 4 * LDQ, aRefl = aTau + 4 * LDQ;
+    const uint32_t aD = aRed + 96, aE = aD + 4 * KN, aTau = aE + 4 * KN, aRefl = aTau + 4 * KN;
     const int lane = tid & 31, warp = tid >> 5;     // logical (rotated) warp: see warp_rotation()
-    for (int j = tid; j < 6 * VL + 24; j += TT) sv[j] = 0.f;
+    for (int j = tid; j < 6 * VL + 24; j += NT) sv[j] = 0.f;
     __syncthreads();
     constexpr int c0 = QD - 1;
     float xi, ri, yi = 0.f;
@@ -359,9 +370,9 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((QD + 3) / 4)], fl
         }
         yi = ((y0.x + y0.y) + (y1.x + y1.y)) + ((y2.x + y2.y) + (y3.x + y3.y));
     }
-    for (int c = QD - 1; c >= 2; --c) {
+    for (int c = QD - 1; c >= CEND; --c) {
         if (32 * warp > c) break;                  // this warp's rows are all eliminated: it leaves (named barriers below)
-        const int k = QD - 1 - c;
+        const int k = QD - 1 - c;                  // step index inside the phase (global: K0 + k)
         const int nb2 = (c + 7) >> 3;              // live 8-column blocks
         const int nthr = 32 * ((c >> 5) + 1);      // threads of the warps still in the loop
         const uint32_t pp = k & 1;
@@ -409,7 +420,7 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((QD + 3) / 4)], fl
         if (active) {
             sts32(aV + 4 * tid, vi);
             sts32(aW + 4 * tid, wi);
-            sts32(aRefl + 4 * (k * (QD - 1) - (k * (k - 1)) / 2 + (c - 1 - tid)), vi);
+            sts32(aRefl + 4 * (refl_off(QDG, K0 + k) - R0 + (c - 1 - tid)), vi);
             sts32(aXn + 4 * tid, (tid < c - 1) ? xnext : 0.f);
             sts32(aRn + 4 * tid, rnext);
             if (tid == c - 1) sts32(aRdn + 24, xnext);    // B[c-1][c-1]: the next diagonal entry
@@ -458,18 +469,34 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((QD + 3) / 4)], fl
         xi = (tid < c - 1) ? xnext : 0.f;
         ri = rnext;
     }
-    // the last 2 x 2 block: B[1][1], B[1][0], B[0][0]
-    if (tid == 1) { sts32(aD + 4 * (QD - 2), b[0].y); sts32(aE + 4 * (QD - 2), b[0].x); sts32(aTau + 4 * (QD - 2), 0.f); }
-    if (tid == 0) { sts32(aD + 4 * (QD - 1), b[0].x); sts32(aE + 4 * (QD - 1), 0.f); sts32(aTau + 4 * (QD - 1), 0.f); }
+    if constexpr (CEND == 2) {   // the last 2 x 2 block: B[1][1], B[1][0], B[0][0]
+        if (tid == 1) { sts32(aD + 4 * (QD - 2), b[0].y); sts32(aE + 4 * (QD - 2), b[0].x); sts32(aTau + 4 * (QD - 2), 0.f); }
+        if (tid == 0) { sts32(aD + 4 * (QD - 1), b[0].x); sts32(aE + 4 * (QD - 1), 0.f); sts32(aTau + 4 * (QD - 1), 0.f); }
+    } else {                     // trailing CEND x CEND matrix for the next phase: row t at trail + t * round4(CEND)
+        constexpr int LDT = (CEND + 3) & ~3;
+        if (tid < CEND) {
+#pragma unroll
+            for (int I = 0; I < LDT / 4; ++I)
+                reinterpret_cast<float4 *>(trail + tid * LDT)[I] = make_float4(b[2 * I].x, b[2 * I].y, b[2 * I + 1].x, b[2 * I + 1].y);
+        }
+    }
     __syncthreads();
-    // flush (d, e, tau | reflectors) to the workspace, coalesced
-    float4 *o4 = reinterpret_cast<float4 *>(out);
+    // flush this phase's (d, e, tau | reflectors) to the workspace
+    constexpr int NK = K1 - K0 + 1 + (CEND == 2 ? 2 : 0);
     const float *sd = sv + 6 * VL + 24;
-    for (int idx = threadIdx.x; idx < 3 * (LDQ / 4); idx += TT) o4[idx] = reinterpret_cast<const float4 *>(sd)[idx];
-    for (int idx = threadIdx.x; idx < NREF / 4; idx += TT) o4[LDQ + idx] = reinterpret_cast<const float4 *>(sd + 3 * LDQ)[idx];
+    for (int idx = threadIdx.x; idx < NK; idx += NT) {
+        out[K0 + idx] = sd[idx];
+        out[LDG + K0 + idx] = sd[KN + idx];
+        out[2 * LDG + K0 + idx] = sd[2 * KN + idx];
+    }
+    for (int idx = threadIdx.x; idx < R1 - R0; idx += NT) out[4 * LDG + R0 + idx] = sd[3 * KN + idx];
 }
 
-template <int QD> constexpr int split_ws_stride() { return 4 * ((QD + 3) & ~3) + ((((QD - 1) * QD / 2) + 3) & ~3); }
+// Workspace per problem (floats): d[LDG] e[LDG] tau[LDG] mean[LDG] reflectors[nref] trailing matrix[NR2 x NR2];
+// tau[LDG-1] doubles as the "problem is valid" flag between the kernels of the split path.
+constexpr int SPLIT_NR2 = 64;                      // trailing size handed from phase 1 to phase 2
+template <int QD> __host__ __device__ constexpr int split_trail_off() { return 4 * ((QD + 3) & ~3) + ((((QD - 1) * QD / 2) + 3) & ~3); }
+template <int QD> __host__ __device__ constexpr int split_ws_stride() { return split_trail_off<QD>() + SPLIT_NR2 * SPLIT_NR2; }
 
 template <bool FUSED, int QD>
 __global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
@@ -479,9 +506,12 @@ __global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
     const int n = P.k, ps = P.ps, ps2 = ps * ps, C = P.c;
     const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + warp_rotation()) & (TT / 32 - 1), tid = 32 * warp + lane;
     const int g = blockIdx.x / C, ch = blockIdx.x - g * C;
-    if (a.inds && !row_valid_block(a.inds + (long long)g * n, n)) return;
+    float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
+    const bool valid_row = !a.inds || row_valid_block(a.inds + (long long)g * n, n);
+    if (threadIdx.x == 0) wsp[3 * LDQ - 1] = valid_row ? 1.f : 0.f;   // flag for tridiag_tail_kernel
+    if (!valid_row) return;
     float *Y = sm;                                   // Y[n][LDQ]: patches, columns reversed (column j = patch element QD-1-j)
-    const int ybody = max(n * LDQ, tridiag_scratch_floats<QD>());
+    const int ybody = max(n * LDQ, tridiag_scratch_floats<QD, QD, SPLIT_NR2>());
     int *pb = (int *)(sm + ybody);                   // fused: offset of the patch corner in the image
     float *sv = sm;                                  // the tridiagonalisation's vectors re-use the head of Y
     const int rstride = P.pt * C * ps2;
@@ -494,7 +524,10 @@ __global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
             bad |= (t < 0 || t + P.pt > a.T || y + ps > a.H || x + ps > a.W);
             pb[nn] = (int)((long long)t * CHW + (long long)y * a.W + x);
         }
-        if (__syncthreads_or(bad)) return;           // malformed index: the group is skipped (bayes_kernel does the same)
+        if (__syncthreads_or(bad)) {                 // malformed index: the group is skipped (bayes_kernel does the same)
+            if (threadIdx.x == 0) wsp[3 * LDQ - 1] = 0.f;
+            return;
+        }
     }
     auto col_off = [&](int j) -> int {
         const int dt = j / ps2, r = j - dt * ps2;
@@ -519,7 +552,6 @@ __global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
     __syncthreads();
     // ---- centre (same summation order as bayes_kernel: 4 interleaved partial sums)
     const float inv_n = 1.f / (float)n;
-    float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
     if (tid < LDQ) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int nn = 0;
@@ -564,7 +596,28 @@ __global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
         __syncthreads();
         if (tid == 0) atomicAdd(&a.rank_var[g], ((red[0] + red[1]) + (red[2] + red[3])) / (float)C);
     }
-    tridiag_regs<QD>(b, sv, wsp, tid);
+    tridiag_regs<QD, QD, SPLIT_NR2, TT>(b, sv, wsp, wsp + split_trail_off<QD>(), tid);
+}
+
+// Split path, second kernel: phase 2 of the tridiagonalisation on the NR x NR trailing matrix, 64 threads and
+// ~110 registers => 8 CTAs per SM for the 62 short, latency-bound steps that remain.
+template <int QDG, int NR>
+__global__ void __launch_bounds__(64, 8) tridiag_tail_kernel(const BayesArgs a) {
+    constexpr int LDG = (QDG + 3) & ~3, NCH = NR / 4;
+    static_assert(NR % 4 == 0 && NR <= 64, "tridiag_tail_kernel: one row per thread of 2 warps");
+    extern __shared__ __align__(16) float sm[];
+    float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
+    if (wsp[3 * LDG - 1] == 0.f) return;              // group skipped by cov_tridiag_kernel
+    const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + warp_rotation()) & 1, tid = 32 * warp + lane;
+    const float4 *tr = reinterpret_cast<const float4 *>(wsp + split_trail_off<QDG>() + min(tid, NR - 1) * NR);
+    float2 b[2 * NCH];
+#pragma unroll
+    for (int I = 0; I < NCH; ++I) {
+        const float4 f = tr[I];
+        b[2 * I] = make_float2(f.x, f.y);
+        b[2 * I + 1] = make_float2(f.z, f.w);
+    }
+    tridiag_regs<QDG, NR, 2, 64>(b, sm, wsp, nullptr, tid);
 }
 
 // SPLIT: phases 0-1 were done by cov_tridiag_kernel; (d, e, tau, mean, packed reflectors) come from the workspace.
@@ -1205,14 +1258,18 @@ static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t 
         const size_t bytes = (size_t)B * p->c * a.ws_stride * sizeof(float);
         a.ws = split_workspace(bytes, st);
         if (!a.ws) { set_error("%s: workspace of %zu bytes: %s", what, bytes, cudaGetErrorString(cudaGetLastError())); return VNLB_ERR_CUDA; }
-        const int ybody = a.L.n * 100 > tridiag_scratch_floats<QD>() ? a.L.n * 100 : tridiag_scratch_floats<QD>();
+        constexpr int scr1 = tridiag_scratch_floats<QD, QD, SPLIT_NR2>();
+        const int ybody = a.L.n * 100 > scr1 ? a.L.n * 100 : scr1;
         const size_t smem1 = (size_t)(ybody + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
         auto k1 = cov_tridiag_kernel<FUSED, QD>;
+        auto k1b = tridiag_tail_kernel<QD, SPLIT_NR2>;
+        const size_t smem1b = (size_t)tridiag_scratch_floats<QD, SPLIT_NR2, 2>() * sizeof(float);
         auto k2 = bayes_kernel<FUSED, false, true>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
         k1<<<B * p->c, TT, smem1, st>>>(a);
+        k1b<<<B * p->c, 64, smem1b, st>>>(a);
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
         return check_launch(what);
     }
