@@ -144,6 +144,13 @@ int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8_t *flat, c
                       int B, const VnlbBayesParams *p, float *rank_var, void *ws, size_t ws_bytes,
                       void *stream);
 
+/* Implementation switch of vnlb_bayes_filter / vnlb_bayes_aggregate_fused for the production patch shape of
+ * step 1 (7x7x2, k = 100: a 98 x 98 eigenproblem per channel): on (default) = covariance + Householder
+ * tridiagonalisation with the matrix in registers, in two phase kernels, followed by the eigen/filter
+ * kernel; off = everything in one shared-memory kernel.  Same algorithm; results agree to rounding.
+ * Returns the previous setting.  (Environment: VNLB_BAYES_SPLIT=0 disables at start-up.) */
+int vnlb_set_bayes_split(int on);
+
 /* Fusion of vpss.fill_patches (search.py:91-98) + exec_flat_areas
  * (flat_areas.py:16-34) + bayes_est.denoise (bayes_est.py:17-62) + agg_patches
  * (comp_agg.py:47-138) for one round of groups: patches are gathered from the

@@ -416,6 +416,51 @@ def test_fused_kernel_matches_staged_pipeline_and_oracle(vb, step):
     assert np.abs(sd.cpu().numpy() - fd).max() <= 2e-5 * np.abs(fd).max()
 
 
+@pytest.mark.parametrize("kind", ["noise", "lowrank", "constant", "duplicates"])
+def test_bayes_split_path_matches_single_kernel_and_oracle(vb, kind):
+    """Step-1 production shape (7x7x2, k = 100): the split path (register-resident tridiagonalisation in two
+    phase kernels, vnlb_set_bayes_split(1)) == the single shared-memory kernel == the oracle, also on
+    degenerate stacks (rank-deficient, constant, duplicated patches: zero columns in the Householder steps)."""
+    from vnlb_b200 import _lib, deno
+    from vnlb_b200.utils import AttrDict
+    a_gpu, a_cpu = gargs(vb, 0), oargs(0)
+    rs = np.random.RandomState(11)
+    B, k = 24, a_cpu.npatches
+    shape = (B, k, 2, 3, 7, 7)
+    if kind == "noise":
+        pn = (rs.rand(*shape) * 255).astype(np.float32)
+    elif kind == "lowrank":                       # 5 patch prototypes + small noise: a few large eigenvalues
+        proto = rs.rand(B, 5, 2, 3, 7, 7).astype(np.float32) * 255
+        mix = rs.rand(B, k, 5).astype(np.float32)
+        pn = np.einsum("bkr,brtchw->bktchw", mix, proto).astype(np.float32) + rs.randn(*shape).astype(np.float32) * 20
+    elif kind == "constant":                      # zero covariance: every Householder step is skipped
+        pn = np.full(shape, 37.5, np.float32)
+        pn[1::2] += rs.randn(B // 2, 1, 2, 3, 7, 7).astype(np.float32) * 30     # identical patches inside a group
+    else:                                         # each patch appears twice: rank <= 50
+        half = (rs.rand(B, k // 2, 2, 3, 7, 7) * 255).astype(np.float32)
+        pn = np.concatenate([half, half], 1)
+    ref, _, _ = orc.bayes_denoise(pn.copy(), np.zeros_like(pn), np.zeros(B, bool), a_cpu)
+    outs = {}
+    for split in (1, 0):
+        prev = _lib.lib.vnlb_set_bayes_split(split)
+        try:
+            patches = AttrDict(noisy=cu(pn.copy()), basic=torch.zeros(shape, device=DEV),
+                               flat=torch.zeros(B, dtype=torch.uint8, device=DEV))
+            rv = deno.denoise(patches, a_gpu, "bayes", None)
+            outs[split] = (patches.noisy.cpu().numpy(), rv.cpu().numpy())
+        finally:
+            _lib.lib.vnlb_set_bayes_split(prev)
+    for split in (1, 0):
+        out, rv = outs[split]
+        assert np.isfinite(out).all(), (kind, split)
+        for b in range(B):
+            den = max(np.linalg.norm(ref[b]), 1e-20)
+            assert np.linalg.norm(out[b] - ref[b]) / den < 1e-4, (kind, split, b)
+    np.testing.assert_allclose(outs[1][1], outs[0][1], rtol=1e-6)          # rank_var: same covariance bits
+    scale = np.abs(outs[0][0]).max()
+    assert np.abs(outs[1][0] - outs[0][0]).max() <= 2e-4 * scale
+
+
 def test_e2e_fast_schedule_psnr(vb, golden_dir):
     """The throughput schedule (fused and staged) stays within the PSNR band of the parity run."""
     g = np.load(os.path.join(golden_dir, "e2e.npz"))

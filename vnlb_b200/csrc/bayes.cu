@@ -7,6 +7,7 @@ int launch_bayes_jacobi(float *pnoisy, const float *pbasic, const unsigned char 
 int launch_bayes_tridiag(float *pnoisy, const float *pbasic, const unsigned char *flat, const long long *inds, int B,
                          const VnlbBayesParams *p, float *rank_var, cudaStream_t st);
 bool bayes_tridiag_supported(const VnlbBayesParams *p);
+int set_bayes_split(int on);
 int launch_bayes_fused(const float *img_noisy, const float *img_basic, const long long *inds, int B, int T, int H,
                        int W, const VnlbBayesParams *p, float flat_thresh, float *deno, float *weights,
                        cudaStream_t st);
@@ -48,6 +49,8 @@ extern "C" int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8
             return VNLB_ERR_BAD_ARG;
     }
 }
+
+extern "C" int vnlb_set_bayes_split(int on) { return set_bayes_split(on); }
 
 extern "C" int vnlb_bayes_fused_supported(const VnlbBayesParams *p) { return p && bayes_tridiag_supported(p) ? 1 : 0; }
 

@@ -540,13 +540,27 @@ __global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) co[q] = col_off(min(lane + 32 * q, QD - 1));
     // ---- stage all n patches (every load independent: one exposed latency)
-    for (int nn = warp; nn < n; nn += TT / 32) {
-        const float *q = src + (FUSED ? (long long)pb[nn] : (long long)nn * rstride);
+    constexpr int SU = 5;                            // patches in flight per warp (20 independent loads per lane)
+    for (int n0 = warp; n0 < n; n0 += SU * (TT / 32)) {
+        float vals[SU][4];
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-            const int j = lane + 32 * qq;
-            if (j < QD) Y[nn * LDQ + (QD - 1 - j)] = q[co[qq]];
-            else if (j < LDQ) Y[nn * LDQ + j] = 0.f;                                 // zero pad columns QD..LDQ-1
+        for (int u = 0; u < SU; ++u) {
+            const int nn = min(n0 + u * (TT / 32), n - 1);
+            const float *q = src + (FUSED ? (long long)pb[nn] : (long long)nn * rstride);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) vals[u][qq] = (lane + 32 * qq < QD) ? q[co[qq]] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int nn = n0 + u * (TT / 32);
+            if (nn < n) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int j = lane + 32 * qq;
+                    if (j < QD) Y[nn * LDQ + (QD - 1 - j)] = vals[u][qq];
+                    else if (j < LDQ) Y[nn * LDQ + j] = 0.f;                         // zero pad columns QD..LDQ-1
+                }
+            }
         }
     }
     __syncthreads();
@@ -1015,7 +1029,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 if (fabsf(dp) < pm) dp = -pm;
                 z[0] = dp;
                 for (int i = 0; i < qd - 1; ++i) {
-                    dp = (d[i + 1] - l) - e2[i + 1] / dp;
+                    dp = (d[i + 1] - l) - __fdividef(e2[i + 1], dp);   // 2-ulp division: the chain's latency is the phase's cost
                     if (fabsf(dp) < pm) dp = -pm;
                     z[i + 1] = dp;
                 }
@@ -1024,7 +1038,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 float best = fabsf(z[qd - 1]);
                 int r = qd - 1;
                 for (int i = qd - 2; i >= 0; --i) {
-                    dm = (d[i] - l) - e2[i + 1] / dm;
+                    dm = (d[i] - l) - __fdividef(e2[i + 1], dm);
                     if (fabsf(dm) < pm) dm = -pm;
                     const float gam = fabsf(z[i] + dm - (d[i] - l));
                     if (gam < best) { best = gam; r = i; }
@@ -1033,7 +1047,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 if (fabsf(dm) < pm) dm = -pm;
                 if (r < qd - 1) z[qd - 1] = dm;
                 for (int i = qd - 2; i > r; --i) {
-                    dm = (d[i] - l) - e2[i + 1] / dm;
+                    dm = (d[i] - l) - __fdividef(e2[i + 1], dm);
                     if (fabsf(dm) < pm) dm = -pm;
                     z[i] = dm;
                 }
@@ -1209,10 +1223,15 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
 
 // Split path (cov_tridiag_kernel + bayes_kernel<.., SPLIT>) for the production shape of step 1 (7x7x2 patches: q = 98,
 // direct covariance); VNLB_BAYES_SPLIT=0 forces the single-kernel shared-memory path.
+static int g_split = -1;   // -1: not read yet; VNLB_BAYES_SPLIT=0 in the environment or vnlb_set_bayes_split(0) disables
 static bool use_split(const TriLayout &L) {
-    static int v = -1;
-    if (v < 0) { const char *s = getenv("VNLB_BAYES_SPLIT"); v = (s && s[0] == '0') ? 0 : 1; }
-    return v != 0 && !L.gram && L.q == 98 && (size_t)(L.n * 100 + L.n + 16) * sizeof(float) <= 72 * 1024;
+    if (g_split < 0) { const char *s = getenv("VNLB_BAYES_SPLIT"); g_split = (s && s[0] == '0') ? 0 : 1; }
+    return g_split != 0 && !L.gram && L.q == 98 && (size_t)(L.n * 100 + L.n + 16) * sizeof(float) <= 72 * 1024;
+}
+int set_bayes_split(int on) {
+    const int prev = g_split < 0 ? 1 : g_split;
+    g_split = on ? 1 : 0;
+    return prev;
 }
 
 // Workspace of the split path: one grow-only buffer per (device, stream), so that the two kernels of a call and
