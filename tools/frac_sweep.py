@@ -4,7 +4,7 @@ import numpy as np, torch, vnlb_b200
 from vnlb_b200 import synth
 T, H, W = 20, 480, 854
 clean = synth.synth_video(T, H, W); noisy = torch.from_numpy(synth.add_noise(clean, 20.)).cuda()
-for frac, qmin, cap in [(1/8, 4096, 16384), (1/16, 4096, 16384), (1/32, 4096, 16384), (1/32, 2048, 16384), (1/64, 2048, 16384), (1/16, 2048, 16384)]:
+for frac, qmin, cap in [(1/8, 4096, 16384), (1/12, 4096, 16384), (1/16, 4096, 16384), (1/16, 2048, 16384), (1/24, 2048, 16384), (1/32, 2048, 16384), (1/12, 4096, 8192), (1/16, 2048, 8192)]:
     params = vnlb_b200.get_params(20.)
     params["fast_frac"] = [frac, frac]; params["fast_min"] = [qmin, qmin]; params["fast_cap"] = [cap, cap]
     for it in range(3):

@@ -46,10 +46,10 @@ struct TriLayout {
     int gram;                      // 1: eigen-decompose the n x n Gram matrix Y Y^T/n instead of the p x p covariance
     int q, LDq, ZSq;               // dimension of the eigenproblem and its pitches
     int oR, rsize, oZ, oVt, oX, xrows;  // inside R: packed reflectors at 0, Z at oZ; later (Ut at 0,) Vt at oVt, X at oX
-    int oD, oE, oE2, oTau, oV, oW, oMean, oLam, oCoef, oLo, oHi, oNlo, oNhi, oRed, oPb, total;
+    int oD, oE, oE2, oTau, oV, oW, oMean, oLam, oCoef, oLo, oHi, oNlo, oNhi, oRed, oT, oPb, total;
 };
 
-static TriLayout tri_layout(int n, int p) {
+static TriLayout tri_layout(int n, int p, bool split = false) {
     TriLayout L;
     L.p = p; L.n = n;
     L.LD = (p + 3) & ~3;
@@ -67,8 +67,9 @@ static TriLayout tri_layout(int n, int p) {
         L.oVt = 0;                                          // Vt[p][MR] at the head of R
         L.oX = (p * MR + 3) & ~3;                           // X[xrows][XS] behind it
         L.oZ = nref > L.oX ? nref : L.oX;                   // Z must not overlap the reflectors nor Vt
-        rsize = L.LD * L.LD;
-        if (rsize < CH * L.LD) rsize = CH * L.LD;
+        rsize = split ? 0 : L.LD * L.LD;                    // split path: the matrix never enters this kernel
+        if (!split && rsize < CH * L.LD) rsize = CH * L.LD;
+        if (rsize < nref) rsize = nref;
         if (rsize < L.oZ + MR * L.ZSq) rsize = L.oZ + MR * L.ZSq;
         const int want_rows = n < 32 ? n : 32;
         if (rsize < L.oX + want_rows * L.XS) rsize = L.oX + want_rows * L.XS;
@@ -109,6 +110,8 @@ static TriLayout tri_layout(int n, int p) {
     L.oNlo = o; o += MR;
     L.oNhi = o; o += MR;
     L.oRed = o; o += 16;
+    L.oT = o; o += 10 * ((vlen + 3) / 4) + 2;               // compact-WY factors of the back-transformation: 10 floats per block of 4 reflectors
+    o = (o + 3) & ~3;
     L.oPb = o; o += 2 * ((n + 3) & ~3);                     // fused mode: per-patch image / weight offsets
     L.total = o;
     return L;
@@ -1070,29 +1073,92 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 } else {                                 // overflow guard (never seen): fall back to the twist basis vector
                     for (int i = 0; i < qd; ++i) z[i] = (i == r) ? 1.f : 0.f;
                 }
+            } else if (32 * warp >= m) {
+                // meanwhile the idle warps form the Gram entries of the reflector blocks (phase 4): g_lj = v_l^T v_j
+                const int first = 32 * ((m + 31) >> 5), nidle = TT - first, nblk = (qd - 2) >> 2;
+                float *Tf = sm + L.oT;
+                for (int idx = tid - first; idx < 6 * nblk; idx += nidle) {
+                    const int blk = idx / 6, pr = idx - 6 * blk;
+                    const int jj = pr < 1 ? 1 : (pr < 3 ? 2 : 3), ll = pr - (jj == 1 ? 0 : (jj == 2 ? 1 : 3));
+                    const int kl = 4 * blk + ll, kj = 4 * blk + jj;
+                    const float *vl = R + (kl * (qd - 1) - (kl * (kl - 1)) / 2) - (kl + 1);
+                    const float *vj = R + (kj * (qd - 1) - (kj * (kj - 1)) / 2) - (kj + 1);
+                    float g0 = 0.f, g1 = 0.f;
+                    int i = kj + 1;
+                    for (; i + 1 < qd; i += 2) { g0 = fmaf(vl[i], vj[i], g0); g1 = fmaf(vl[i + 1], vj[i + 1], g1); }
+                    if (i < qd) g0 = fmaf(vl[i], vj[i], g0);
+                    Tf[10 * blk + pr] = g0 + g1;
+                }
             }
             __syncthreads();
 
             // ---------------------------------------------------------- 4. back-transformation  z <- H_0 ... H_{qd-3} z
+            // Blocks of 4 reflectors in compact-WY form, H_a H_{a+1} H_{a+2} H_{a+3} = I - V T V^T (T upper triangular,
+            // LAPACK dlarft forward/columnwise): 4 dot products reduced together, one small triangular product, one
+            // fused update -- a quarter of the dependent shuffle chains of reflector-by-reflector application.
+            // The Gram entries g_lj = v_l^T v_j were formed by the idle warps during the twisted factorisation.
             {
+                const int nrefl = qd - 2, nblk = nrefl >> 2, rem = nrefl - 4 * nblk;   // blocks cover k = 0 .. 4 nblk - 1
+                float *Tf = sm + L.oT;
+                if (tid < nblk) {
+                    float *g = Tf + 10 * tid;
+                    const float g01 = g[0], g02 = g[1], g12 = g[2], g03 = g[3], g13 = g[4], g23 = g[5];
+                    const float t0 = taus[4 * tid], t1 = taus[4 * tid + 1], t2 = taus[4 * tid + 2], t3 = taus[4 * tid + 3];
+                    const float T01 = -t1 * (t0 * g01);
+                    const float T02 = -t2 * fmaf(T01, g12, t0 * g02), T12 = -t2 * (t1 * g12);
+                    const float T03 = -t3 * fmaf(T02, g23, fmaf(T01, g13, t0 * g03)), T13 = -t3 * fmaf(T12, g23, t1 * g13), T23 = -t3 * (t2 * g23);
+                    g[0] = t0; g[1] = T01; g[2] = T02; g[3] = T03; g[4] = t1; g[5] = T12; g[6] = T13; g[7] = t2; g[8] = T23; g[9] = t3;
+                }
+                __syncthreads();
                 int S = 2;                                   // lanes per eigenvector (power of two, S*m <= 128)
                 while (S * 2 * m <= TT && S < 32) S *= 2;
                 const int vec = tid / S, part = tid - vec * S;
                 const bool on = vec < m;
                 float *z = Z + min(vec, m - 1) * ZSq;
-                for (int k = qd - 3; k >= 0; --k) {
+                for (int k = qd - 3; k >= 4 * nblk; --k) {   // the (at most 3) shortest reflectors, one by one
                     const float tau = taus[k];
                     if (tau == 0.f) continue;
                     const float *vr = R + (k * (qd - 1) - (k * (k - 1)) / 2) - (k + 1);   // vr[i], i = k+1..qd-1
-                    float s0 = 0.f, s1 = 0.f;
-                    int i = k + 1 + part;
-                    for (; i + S < qd; i += 2 * S) { s0 = fmaf(vr[i], z[i], s0); s1 = fmaf(vr[i + S], z[i + S], s1); }
-                    if (i < qd) s0 = fmaf(vr[i], z[i], s0);
-                    float s = s0 + s1;
+                    float s = 0.f;
+                    for (int i = k + 1 + part; i < qd; i += S) s = fmaf(vr[i], z[i], s);
                     for (int dlt = S >> 1; dlt > 0; dlt >>= 1) s += __shfl_xor_sync(0xffffffffu, s, dlt);
                     s *= tau;
                     if (on)
                         for (int ii = k + 1 + part; ii < qd; ii += S) z[ii] = fmaf(-s, vr[ii], z[ii]);
+                    __syncwarp();
+                }
+                (void)rem;
+                for (int bk = nblk - 1; bk >= 0; --bk) {
+                    const int a0 = 4 * bk;
+                    const float *v0 = R + (a0 * (qd - 1) - (a0 * (a0 - 1)) / 2) - (a0 + 1);       // v_{a0}[i], i >= a0+1
+                    const float *v1 = v0 + (qd - 1 - a0) - 1;                                          // v_{a0+1}[i], i >= a0+2
+                    const float *v2 = v1 + (qd - 2 - a0) - 1;
+                    const float *v3 = v2 + (qd - 3 - a0) - 1;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    for (int i = a0 + 1 + part; i < qd; i += S) {
+                        const float zi = z[i];
+                        s0 = fmaf(v0[i], zi, s0);
+                        if (i > a0 + 1) s1 = fmaf(v1[i], zi, s1);
+                        if (i > a0 + 2) s2 = fmaf(v2[i], zi, s2);
+                        if (i > a0 + 3) s3 = fmaf(v3[i], zi, s3);
+                    }
+                    for (int dlt = S >> 1; dlt > 0; dlt >>= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, dlt); s1 += __shfl_xor_sync(0xffffffffu, s1, dlt);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, dlt); s3 += __shfl_xor_sync(0xffffffffu, s3, dlt);
+                    }
+                    const float *T = Tf + 10 * bk;
+                    const float u3 = T[9] * s3;
+                    const float u2 = fmaf(T[8], s3, T[7] * s2);
+                    const float u1 = fmaf(T[6], s3, fmaf(T[5], s2, T[4] * s1));
+                    const float u0 = fmaf(T[3], s3, fmaf(T[2], s2, fmaf(T[1], s1, T[0] * s0)));
+                    if (on)
+                        for (int i = a0 + 1 + part; i < qd; i += S) {
+                            float zi = fmaf(-u0, v0[i], z[i]);
+                            if (i > a0 + 1) zi = fmaf(-u1, v1[i], zi);
+                            if (i > a0 + 2) zi = fmaf(-u2, v2[i], zi);
+                            if (i > a0 + 3) zi = fmaf(-u3, v3[i], zi);
+                            z[i] = zi;
+                        }
                     __syncwarp();
                 }
             }
@@ -1269,9 +1335,10 @@ static float *split_workspace(size_t bytes, cudaStream_t st) {
 template <bool FUSED>
 static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t st) {
     const VnlbBayesParams *p = &a.P;
-    const size_t smem = (size_t)a.L.total * sizeof(float);
     cudaError_t e;
     if (use_split(a.L)) {
+        a.L = tri_layout(a.L.n, a.L.p, true);            // no covariance matrix in the eigen/filter kernel
+        const size_t smem = (size_t)a.L.total * sizeof(float);
         constexpr int QD = 98;
         a.ws_stride = split_ws_stride<QD>();
         const size_t bytes = (size_t)B * p->c * a.ws_stride * sizeof(float);
@@ -1292,6 +1359,7 @@ static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t 
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
         return check_launch(what);
     }
+    const size_t smem = (size_t)a.L.total * sizeof(float);
     auto kern = a.L.gram ? bayes_kernel<FUSED, true, false> : bayes_kernel<FUSED, false, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
