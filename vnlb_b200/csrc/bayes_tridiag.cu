@@ -1024,6 +1024,95 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
             __syncthreads();
 
             // ---------------------------------------------------------- 3. eigenvectors of T (twisted factorisation)
+            // g_work: the warps that hold no eigenpair form the Gram entries of the reflector blocks (phase 4): g_lj = v_l^T v_j
+            auto g_work = [&](int first) {
+                const int nidle = TT - first, nblk = (qd - 2) >> 2;
+                float *Tf = sm + L.oT;
+                for (int idx = tid - first; idx < 6 * nblk; idx += nidle) {
+                    const int blk = idx / 6, pr = idx - 6 * blk;
+                    const int jj = pr < 1 ? 1 : (pr < 3 ? 2 : 3), ll = pr - (jj == 1 ? 0 : (jj == 2 ? 1 : 3));
+                    const int kl = 4 * blk + ll, kj = 4 * blk + jj;
+                    const float *vl = R + (kl * (qd - 1) - (kl * (kl - 1)) / 2) - (kl + 1);
+                    const float *vj = R + (kj * (qd - 1) - (kj * (kj - 1)) / 2) - (kj + 1);
+                    float g0 = 0.f, g1 = 0.f;
+                    int i = kj + 1;
+                    for (; i + 1 < qd; i += 2) { g0 = fmaf(vl[i], vj[i], g0); g1 = fmaf(vl[i + 1], vj[i + 1], g1); }
+                    if (i < qd) g0 = fmaf(vl[i], vj[i], g0);
+                    Tf[10 * blk + pr] = g0 + g1;
+                }
+            };
+            if (2 * m <= MR) {
+                // Two threads per eigenpair: thread r runs the forward pivots D+ into row r of Z while thread m + r runs
+                // the backward pivots D- into the spare row m + r -- the two 98-long division chains side by side and no
+                // second backward pass; then both find the twist index, and each solves its side of the eigenvector.
+                const bool fwd = tid < m, bwd = !fwd && tid < 2 * m;
+                const int ev = fwd ? tid : (bwd ? tid - m : 0);
+                float *z = Z + ev * ZSq, *zb = Z + (m + ev) * ZSq;
+                const float l = lam[ev];
+                const float pm = fmaxf(pivmin, 1e-10f * fabsf(l));
+                if (fwd) {
+                    float dp = d[0] - l;
+                    if (fabsf(dp) < pm) dp = -pm;
+                    z[0] = dp;
+                    for (int i = 0; i < qd - 1; ++i) {
+                        dp = (d[i + 1] - l) - __fdividef(e2[i + 1], dp);
+                        if (fabsf(dp) < pm) dp = -pm;
+                        z[i + 1] = dp;
+                    }
+                } else if (bwd) {
+                    float dm = d[qd - 1] - l;
+                    if (fabsf(dm) < pm) dm = -pm;
+                    zb[qd - 1] = dm;
+                    for (int i = qd - 2; i >= 0; --i) {
+                        dm = (d[i] - l) - __fdividef(e2[i + 1], dm);
+                        if (fabsf(dm) < pm) dm = -pm;
+                        zb[i] = dm;
+                    }
+                } else if (32 * warp >= 2 * m) {
+                    g_work(32 * ((2 * m + 31) >> 5));
+                }
+                __syncthreads();
+                float nrm = 0.f;
+                int r = qd - 1;
+                if (fwd || bwd) {
+                    float best = fabsf(z[qd - 1]);        // twist index r = argmin |gamma_i|, gamma_i = D+_i + D-_i - (d_i - l)
+                    for (int i = qd - 2; i >= 0; --i) {
+                        const float gam = fabsf(z[i] + zb[i] - (d[i] - l));
+                        if (gam < best) { best = gam; r = i; }
+                    }
+                }
+                __syncthreads();                           // every D+ / D- has been read before the solves overwrite Z
+                if (fwd) {                                 // z_r = 1; upwards with D+
+                    float zi = 1.f;
+                    nrm = 1.f;
+                    for (int i = r - 1; i >= 0; --i) {
+                        zi = -(e[i] / z[i]) * zi;
+                        z[i] = zi;
+                        nrm = fmaf(zi, zi, nrm);
+                    }
+                    z[r] = 1.f;
+                    blo[ev] = nrm;
+                } else if (bwd) {                          // downwards with D-
+                    float zi = 1.f;
+                    for (int i = r; i < qd - 1; ++i) {
+                        zi = -(e[i] / zb[i + 1]) * zi;
+                        z[i + 1] = zi;
+                        nrm = fmaf(zi, zi, nrm);
+                    }
+                    bhi[ev] = nrm;
+                }
+                __syncthreads();
+                if (fwd || bwd) {
+                    nrm = blo[ev] + bhi[ev];
+                    const float sc = rsqrtf(nrm);
+                    const int i0 = fwd ? 0 : r + 1, i1 = fwd ? r + 1 : qd;
+                    if (nrm < 3.0e38f && sc > 0.f) {
+                        for (int i = i0; i < i1; ++i) z[i] *= sc;
+                    } else {                             // overflow guard (never seen): fall back to the twist basis vector
+                        for (int i = i0; i < i1; ++i) z[i] = (i == r) ? 1.f : 0.f;
+                    }
+                }
+            } else
             if (tid < m) {
                 float *z = Z + tid * ZSq;
                 const float l = lam[tid];
@@ -1074,21 +1163,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                     for (int i = 0; i < qd; ++i) z[i] = (i == r) ? 1.f : 0.f;
                 }
             } else if (32 * warp >= m) {
-                // meanwhile the idle warps form the Gram entries of the reflector blocks (phase 4): g_lj = v_l^T v_j
-                const int first = 32 * ((m + 31) >> 5), nidle = TT - first, nblk = (qd - 2) >> 2;
-                float *Tf = sm + L.oT;
-                for (int idx = tid - first; idx < 6 * nblk; idx += nidle) {
-                    const int blk = idx / 6, pr = idx - 6 * blk;
-                    const int jj = pr < 1 ? 1 : (pr < 3 ? 2 : 3), ll = pr - (jj == 1 ? 0 : (jj == 2 ? 1 : 3));
-                    const int kl = 4 * blk + ll, kj = 4 * blk + jj;
-                    const float *vl = R + (kl * (qd - 1) - (kl * (kl - 1)) / 2) - (kl + 1);
-                    const float *vj = R + (kj * (qd - 1) - (kj * (kj - 1)) / 2) - (kj + 1);
-                    float g0 = 0.f, g1 = 0.f;
-                    int i = kj + 1;
-                    for (; i + 1 < qd; i += 2) { g0 = fmaf(vl[i], vj[i], g0); g1 = fmaf(vl[i + 1], vj[i + 1], g1); }
-                    if (i < qd) g0 = fmaf(vl[i], vj[i], g0);
-                    Tf[10 * blk + pr] = g0 + g1;
-                }
+                g_work(32 * ((m + 31) >> 5));
             }
             __syncthreads();
 
