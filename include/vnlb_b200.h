@@ -79,6 +79,9 @@ typedef struct {
 
 const char *vnlb_last_error(void);
 int vnlb_version(void);
+/* Number of CUDA kernels the library has launched in this process (monotonic; bench.py reports the
+ * difference over the timed region as gpu_launches). */
+unsigned long long vnlb_kernel_launches(void);
 
 /* rgb2yuv_cpp, lib/vnlb/utils/color.py:52-77 (out of place; src may equal dst). */
 int vnlb_rgb2yuv(const float *rgb, float *yuv, int T, int C, int H, int W, void *stream);

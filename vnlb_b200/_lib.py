@@ -33,6 +33,7 @@ class BayesParams(ctypes.Structure):
 
 
 EXPORTS = [
+    "vnlb_kernel_launches",
     "vnlb_last_error", "vnlb_version", "vnlb_rgb2yuv", "vnlb_yuv2rgb", "vnlb_init_mask",
     "vnlb_search_workspace_bytes", "vnlb_search_topk", "vnlb_fill_patches", "vnlb_mask_update",
     "vnlb_count_mask", "vnlb_select_queries", "vnlb_pad_queries",
@@ -49,6 +50,7 @@ lib = ctypes.CDLL(LIB_PATH)
 lib.vnlb_last_error.restype = ctypes.c_char_p
 lib.vnlb_search_workspace_bytes.restype = ctypes.c_size_t
 lib.vnlb_bayes_workspace_bytes.restype = ctypes.c_size_t
+lib.vnlb_kernel_launches.restype = ctypes.c_ulonglong
 for _name in EXPORTS:
     getattr(lib, _name)  # fail at import if a declared symbol is not exported
 

@@ -1290,6 +1290,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
 #pragma unroll
             for (int q = 0; q < 4; ++q) co[q] = col_off(min(lane + 32 * q, p - 1), ch);
         }
+
         // centre of the noisy patches: mean_n(noisy), or cbasic for a flat group in step 2 (bayes_est.py:88-104)
         if (P.cov_from_basic ? !is_flat : false) {
             for (int j = tid; j < p; j += TT) {
@@ -1311,12 +1312,29 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
         __syncthreads();
         for (int c0 = 0; c0 < n; c0 += L.xrows) {
             const int rows = min(L.xrows, n - c0);
-            for (int nn = warp; nn < rows; nn += TT / 32) {
-                const float *q = base_noisy + row_off(c0 + nn);
+            {   // gather with 4 patches (16 independent loads per lane) in flight
+                float mj[4];
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const int j = lane + 32 * qq;
-                    if (j < p) X[nn * XS + j] = q[co[qq]] - mean[j];
+                for (int qq = 0; qq < 4; ++qq) mj[qq] = mean[min(lane + 32 * qq, p - 1)];
+                for (int n0 = warp; n0 < rows; n0 += 4 * (TT / 32)) {
+                    float vals[4][4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float *q = base_noisy + row_off(c0 + min(n0 + u * (TT / 32), rows - 1));
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) vals[u][qq] = q[co[qq]];       // co[] is clamped to column p-1
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int nn = n0 + u * (TT / 32);
+                        if (nn < rows) {
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq) {
+                                const int j = lane + 32 * qq;
+                                if (j < p) X[nn * XS + j] = vals[u][qq] - mj[qq];
+                            }
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -1329,6 +1347,14 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 default: filter_chunk<5>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
             }
             __syncthreads();
+            int wo[4] = {0, 0, 0, 0};                    // fused: offsets of this lane's patch elements in `weights`
+            if (FUSED && ch == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = min(lane + 32 * q, p - 1), dt = j / ps2, r = j - dt * ps2, dy = r / ps, dx = r - dy * ps;
+                    wo[q] = (int)(dt * HW + (long long)dy * a.W + dx);
+                }
+            }
             for (int nn = warp; nn < rows; nn += TT / 32) {
                 if (FUSED) {   // agg_patches (lib/vnlb/agg/comp_agg.py:106-138): scatter with float atomics
                     float *q = a.deno + pb[c0 + nn];
@@ -1342,10 +1368,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
 #pragma unroll
                         for (int qq = 0; qq < 4; ++qq) {
                             const int j = lane + 32 * qq;
-                            if (j < p) {
-                                const int dt = j / ps2, r = j - dt * ps2, dy = r / ps, dx = r - dy * ps;
-                                atomicAdd(qw + dt * HW + (long long)dy * a.W + dx, 1.f);
-                            }
+                            if (j < p) atomicAdd(qw + wo[qq], 1.f);
                         }
                     }
                 } else {
@@ -1432,7 +1455,7 @@ static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t 
         k1<<<B * p->c, TT, smem1, st>>>(a);
         k1b<<<B * p->c, 64, smem1b, st>>>(a);
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
-        return check_launch(what);
+        return check_launch(what, 3);
     }
     const size_t smem = (size_t)a.L.total * sizeof(float);
     auto kern = a.L.gram ? bayes_kernel<FUSED, true, false> : bayes_kernel<FUSED, false, false>;

@@ -10,7 +10,11 @@ namespace vnlb {
 
 void set_error(const char *fmt, ...);
 
-inline int check_launch(const char *what) {
+// kernels launched by the library so far (vnlb_kernel_launches); `kernels` = launches the call just made
+extern unsigned long long g_kernel_launches;
+
+inline int check_launch(const char *what, int kernels = 1) {
+    g_kernel_launches += (unsigned long long)kernels;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));

@@ -179,7 +179,9 @@ __global__ void pad_queries_kernel(long long *__restrict__ qinds, const unsigned
 using namespace vnlb;
 
 extern "C" const char *vnlb_last_error(void) { return g_err; }
-extern "C" int vnlb_version(void) { return 100; }
+extern "C" int vnlb_version(void) { return 101; }
+namespace vnlb { unsigned long long g_kernel_launches = 0; }
+extern "C" unsigned long long vnlb_kernel_launches(void) { return vnlb::g_kernel_launches; }
 
 static int grid_for(long long n, int threads) {
     long long b = (n + threads - 1) / threads;
