@@ -697,7 +697,15 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
             float s = 0.f, s2 = 0.f;
             if (tid < p) {
                 const float *q = base_noisy + col_off(tid, ch);
-                for (int nn = 0; nn < n; ++nn) { const float x = q[pb[nn]]; s += x; s2 = fmaf(x, x, s2); }
+                int nn = 0;
+                for (; nn + 7 < n; nn += 8) {          // 8 loads in flight, accumulated in the original order
+                    float x[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) x[u] = q[pb[nn + u]];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { s += x[u]; s2 = fmaf(x[u], x[u], s2); }
+                }
+                for (; nn < n; ++nn) { const float x = q[pb[nn]]; s += x; s2 = fmaf(x, x, s2); }
             }
             const float ts = block_sum(s, red, phase), ts2 = block_sum(s2, red, phase);
             var_sum += (ts2 - ts * ts / (float)Zn) / (float)(Zn - 1);
@@ -734,6 +742,13 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
             if (j < p) {
                 const float *q = src + col_off(j, ch);
                 int nn = 0;
+                for (; nn + 11 < n; nn += 12) {         // 12 loads in flight, same 4 interleaved partial sums
+                    float x[12];
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) x[u] = q[row_off(nn + u)];
+#pragma unroll
+                    for (int u = 0; u < 12; u += 4) { s0 += x[u]; s1 += x[u + 1]; s2 += x[u + 2]; s3 += x[u + 3]; }
+                }
                 for (; nn + 3 < n; nn += 4) {
                     s0 += q[row_off(nn)]; s1 += q[row_off(nn + 1)];
                     s2 += q[row_off(nn + 2)]; s3 += q[row_off(nn + 3)];
@@ -807,8 +822,20 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 const int ncol = min(32, p - 32 * qq);
                 if (ncol <= 0) break;
                 const int j = lane + 32 * qq;
-                for (int nn = warp; nn < LDq; nn += TT / 32)
-                    R[lane * LDq + nn] = (j < p && nn < n) ? src[row_off(nn) + co[qq]] - mean[j] : 0.f;
+                {   // all of this lane's loads of the chunk in flight (LDq <= 60: at most 15 per lane)
+                    float vals[16];
+                    const float mj = mean[min(j, p - 1)];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int nn = warp + u * (TT / 32);
+                        vals[u] = (j < p && nn < n) ? src[row_off(nn) + co[qq]] - mj : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        const int nn = warp + u * (TT / 32);
+                        if (nn < LDq) R[lane * LDq + nn] = vals[u];
+                    }
+                }
                 __syncthreads();
                 for (int l = 0; l < ncol; ++l) {
                     const float *row = R + l * LDq;
@@ -1297,6 +1324,13 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 const float *q = base_noisy + col_off(j, ch);
                 float s0 = 0.f, s1 = 0.f;
                 int nn = 0;
+                for (; nn + 11 < n; nn += 12) {         // 12 loads in flight, same 2 interleaved partial sums
+                    float x[12];
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) x[u] = q[row_off(nn + u)];
+#pragma unroll
+                    for (int u = 0; u < 12; u += 2) { s0 += x[u]; s1 += x[u + 1]; }
+                }
                 for (; nn + 1 < n; nn += 2) { s0 += q[row_off(nn)]; s1 += q[row_off(nn + 1)]; }
                 if (nn < n) s0 += q[row_off(nn)];
                 mean[j] = (s0 + s1) * inv_n;
