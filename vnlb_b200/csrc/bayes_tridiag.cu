@@ -31,6 +31,7 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -312,6 +313,9 @@ __device__ __forceinline__ float lds32(uint32_t a) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ void sts128(uint32_t a, float2 lo, float2 hi) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(lo.x), "f"(lo.y), "f"(hi.x), "f"(hi.y) : "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_newton(float x) {   // 1/x: MUFU.RCP + one Newton step, no special cases
@@ -332,8 +336,10 @@ template <int QDG, int NR, int CEND> __host__ __device__ constexpr int tridiag_s
            ((refl_off(QDG, QDG - CEND) - refl_off(QDG, QDG - NR) + 3) & ~3);
 }
 
-template <int QDG, int NR, int CEND, int NT>
-__device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((NR + 3) / 4)], float *sv, float *out, float *trail, int tid) {
+// NRC = 4-column chunks of a row held in registers; chunks NRC .. NCH-1 (the columns that die first) live in this
+// thread's shared-memory row at byte address aBs: fewer registers => more CTAs per SM for the widest phase.
+template <int QDG, int NR, int CEND, int NT, int NRC = (NR + 3) / 4>
+__device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * NRC], float *sv, float *out, float *trail, int tid, uint32_t aBs = 0) {
     constexpr int QD = NR;
     constexpr int LDQ = (QD + 3) & ~3;
     constexpr int LDG = (QDG + 3) & ~3;
@@ -344,6 +350,13 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((NR + 3) / 4)], fl
     constexpr int KN = (K1 - K0 + 1 + 2 + 3) & ~3;             // + the two trailing entries of the last phase
     constexpr int R0 = refl_off(QDG, K0), R1 = refl_off(QDG, K1 + 1);
     static_assert(NB2 <= 13 && QD >= 8 && CEND >= 2 && CEND < NR, "tridiag_regs: 8 <= NR <= 104");
+    static_assert(NRC <= NCH && (CEND == 2 ? NRC >= 1 : CEND <= 4 * NRC), "tridiag_regs: the trailing matrix handed on must be register resident");
+    // column j of this row: register (static index) or shared memory
+    auto colv = [&](auto jc) -> float {
+        constexpr int j = decltype(jc)::value;
+        if constexpr (j / 4 < NRC) return (j & 1) ? b[j >> 1].y : b[j >> 1].x;
+        else return lds32(aBs + 4 * (j - 4 * NRC));
+    };
     const uint32_t s0 = smem_u32(sv);
     const uint32_t aV = s0 + 16 * VL, aW = s0 + 20 * VL, aRed = s0 + 24 * VL;   // byte addresses
     const uint32_t aD = aRed + 96, aE = aD + 4 * KN, aTau = aE + 4 * KN, aRefl = aTau + 4 * KN;
@@ -353,23 +366,27 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((NR + 3) / 4)], fl
     constexpr int c0 = QD - 1;
     float xi, ri, yi = 0.f;
     {   // columns QD-1 and QD-2 of the untouched matrix
-        const float x0 = (c0 & 1) ? b[c0 >> 1].y : b[c0 >> 1].x;
-        const float r0 = ((c0 - 1) & 1) ? b[(c0 - 1) >> 1].y : b[(c0 - 1) >> 1].x;
+        const float x0 = colv(std::integral_constant<int, c0>()), r0 = colv(std::integral_constant<int, c0 - 1>());
         if (tid < c0) { sts32(s0 + 4 * tid, x0); sts32(s0 + 4 * (VL + tid), r0); }
         if (tid == c0) sts32(aRed + 24, x0);
         xi = tid < c0 ? x0 : 0.f;
         ri = r0;
     }
     int Iw = (c0 - 2) >> 2;                        // the window holds columns 4 Iw .. 4 Iw + 3 of this row
-    float win0 = b[2 * ((c0 - 2) >> 2)].x, win1 = b[2 * ((c0 - 2) >> 2)].y, win2 = b[2 * ((c0 - 2) >> 2) + 1].x, win3 = b[2 * ((c0 - 2) >> 2) + 1].y;
+    constexpr int w0 = 4 * ((c0 - 2) >> 2);
+    float win0 = colv(std::integral_constant<int, w0>()), win1 = colv(std::integral_constant<int, w0 + 1>());
+    float win2 = colv(std::integral_constant<int, w0 + 2>()), win3 = colv(std::integral_constant<int, w0 + 3>());
     __syncthreads();
     if (tid <= c0) {                               // y = B x for the first column
         float2 y0 = make_float2(0.f, 0.f), y1 = y0, y2 = y0, y3 = y0;
 #pragma unroll
         for (int I = 0; I < NCH; ++I) {
             const float4 x4 = lds128(s0 + 16 * I);
-            if (I & 1) { y2 = __ffma2_rn(b[2 * I], make_float2(x4.x, x4.y), y2); y3 = __ffma2_rn(b[2 * I + 1], make_float2(x4.z, x4.w), y3); }
-            else       { y0 = __ffma2_rn(b[2 * I], make_float2(x4.x, x4.y), y0); y1 = __ffma2_rn(b[2 * I + 1], make_float2(x4.z, x4.w), y1); }
+            float2 lo, hi;
+            if (I < NRC) { lo = b[2 * (I < NRC ? I : 0)]; hi = b[2 * (I < NRC ? I : 0) + 1]; }
+            else { const float4 f = lds128(aBs + 16 * (I - NRC)); lo = make_float2(f.x, f.y); hi = make_float2(f.z, f.w); }
+            if (I & 1) { y2 = __ffma2_rn(lo, make_float2(x4.x, x4.y), y2); y3 = __ffma2_rn(hi, make_float2(x4.z, x4.w), y3); }
+            else       { y0 = __ffma2_rn(lo, make_float2(x4.x, x4.y), y0); y1 = __ffma2_rn(hi, make_float2(x4.z, x4.w), y1); }
         }
         yi = ((y0.x + y0.y) + (y1.x + y1.y)) + ((y2.x + y2.y) + (y3.x + y3.y));
     }
@@ -439,10 +456,15 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((NR + 3) / 4)], fl
             if constexpr ((J) < NCH) {                                                  \
                 constexpr int I = (J) < NCH ? (J) : 0;                                  \
                 const float4 v4 = lds128(aV + 16 * I), w4 = lds128(aW + 16 * I), x4 = lds128(aXn + 16 * I);                       \
-                b[2 * I] = __ffma2_rn(nvi, make_float2(w4.x, w4.y), __ffma2_rn(nwi, make_float2(v4.x, v4.y), b[2 * I]));         \
-                b[2 * I + 1] = __ffma2_rn(nvi, make_float2(w4.z, w4.w), __ffma2_rn(nwi, make_float2(v4.z, v4.w), b[2 * I + 1])); \
-                if (I & 1) { y2 = __ffma2_rn(b[2 * I], make_float2(x4.x, x4.y), y2); y3 = __ffma2_rn(b[2 * I + 1], make_float2(x4.z, x4.w), y3); } \
-                else       { y0 = __ffma2_rn(b[2 * I], make_float2(x4.x, x4.y), y0); y1 = __ffma2_rn(b[2 * I + 1], make_float2(x4.z, x4.w), y1); } \
+                float2 lo, hi;                                                          \
+                if constexpr (I < NRC) { lo = b[2 * (I < NRC ? I : 0)]; hi = b[2 * (I < NRC ? I : 0) + 1]; }                      \
+                else { const float4 f = lds128(aBs + 16 * (I - NRC)); lo = make_float2(f.x, f.y); hi = make_float2(f.z, f.w); }   \
+                lo = __ffma2_rn(nvi, make_float2(w4.x, w4.y), __ffma2_rn(nwi, make_float2(v4.x, v4.y), lo));                      \
+                hi = __ffma2_rn(nvi, make_float2(w4.z, w4.w), __ffma2_rn(nwi, make_float2(v4.z, v4.w), hi));                      \
+                if constexpr (I < NRC) { b[2 * (I < NRC ? I : 0)] = lo; b[2 * (I < NRC ? I : 0) + 1] = hi; }                      \
+                else sts128(aBs + 16 * (I - NRC), lo, hi);                              \
+                if (I & 1) { y2 = __ffma2_rn(lo, make_float2(x4.x, x4.y), y2); y3 = __ffma2_rn(hi, make_float2(x4.z, x4.w), y3); } \
+                else       { y0 = __ffma2_rn(lo, make_float2(x4.x, x4.y), y0); y1 = __ffma2_rn(hi, make_float2(x4.z, x4.w), y1); } \
             }
 #define VNLB_SWB(G) case (G) + 1: { VNLB_SW1(2 * (G) + 1) VNLB_SW1(2 * (G)) }
             switch (nb2) {
@@ -461,12 +483,17 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * ((NR + 3) / 4)], fl
         }
         if (c >= 3 && ((c - 3) >> 2) != Iw) {      // next step needs column c-3: re-read the window from the registers
             Iw = (c - 3) >> 2;
-            switch (Iw) {
-#define VNLB_W(J) case (J): if constexpr ((J) < NCH) { win0 = b[2 * ((J) < NCH ? (J) : 0)].x; win1 = b[2 * ((J) < NCH ? (J) : 0)].y; win2 = b[2 * ((J) < NCH ? (J) : 0) + 1].x; win3 = b[2 * ((J) < NCH ? (J) : 0) + 1].y; } break;
-                VNLB_W(0) VNLB_W(1) VNLB_W(2) VNLB_W(3) VNLB_W(4) VNLB_W(5) VNLB_W(6) VNLB_W(7) VNLB_W(8) VNLB_W(9) VNLB_W(10) VNLB_W(11) VNLB_W(12)
-                VNLB_W(13) VNLB_W(14) VNLB_W(15) VNLB_W(16) VNLB_W(17) VNLB_W(18) VNLB_W(19) VNLB_W(20) VNLB_W(21) VNLB_W(22) VNLB_W(23) VNLB_W(24) VNLB_W(25)
+            if (Iw >= NRC) {
+                const float4 f = lds128(aBs + 16 * (Iw - NRC));
+                win0 = f.x; win1 = f.y; win2 = f.z; win3 = f.w;
+            } else {
+                switch (Iw) {
+#define VNLB_W(J) case (J): if constexpr ((J) < NRC) { win0 = b[2 * ((J) < NRC ? (J) : 0)].x; win1 = b[2 * ((J) < NRC ? (J) : 0)].y; win2 = b[2 * ((J) < NRC ? (J) : 0) + 1].x; win3 = b[2 * ((J) < NRC ? (J) : 0) + 1].y; } break;
+                    VNLB_W(0) VNLB_W(1) VNLB_W(2) VNLB_W(3) VNLB_W(4) VNLB_W(5) VNLB_W(6) VNLB_W(7) VNLB_W(8) VNLB_W(9) VNLB_W(10) VNLB_W(11) VNLB_W(12)
+                    VNLB_W(13) VNLB_W(14) VNLB_W(15) VNLB_W(16) VNLB_W(17) VNLB_W(18) VNLB_W(19) VNLB_W(20) VNLB_W(21) VNLB_W(22) VNLB_W(23) VNLB_W(24) VNLB_W(25)
 #undef VNLB_W
-                default: break;
+                    default: break;
+                }
             }
         }
         xi = (tid < c - 1) ? xnext : 0.f;
@@ -501,9 +528,12 @@ constexpr int SPLIT_NR2 = 64;                      // trailing size handed from 
 template <int QD> __host__ __device__ constexpr int split_trail_off() { return 4 * ((QD + 3) & ~3) + ((((QD - 1) * QD / 2) + 3) & ~3); }
 template <int QD> __host__ __device__ constexpr int split_ws_stride() { return split_trail_off<QD>() + SPLIT_NR2 * SPLIT_NR2; }
 
-template <bool FUSED, int QD>
-__global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
-    constexpr int LDQ = (QD + 3) & ~3, NCH = LDQ / 4;
+// NRC: 4-column chunks of a row kept in registers (the rest of the row lives in shared memory until those columns are
+// eliminated): NRC = NCH is everything in registers (166 registers, 3 CTAs per SM), NRC = SPLIT_NR2 / 4 keeps exactly
+// the columns that survive this phase (<= 128 registers, 4 CTAs per SM).
+template <bool FUSED, int QD, int NRC>
+__global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_kernel(const BayesArgs a) {
+    constexpr int LDQ = (QD + 3) & ~3, NCH = LDQ / 4, NSC = NCH - NRC, PH = 4 * NSC;   // NSC chunks per row in shared memory, pitch PH
     extern __shared__ __align__(16) float sm[];
     const VnlbBayesParams &P = a.P;
     const int n = P.k, ps = P.ps, ps2 = ps * ps, C = P.c;
@@ -515,7 +545,8 @@ __global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
     if (!valid_row) return;
     float *Y = sm;                                   // Y[n][LDQ]: patches, columns reversed (column j = patch element QD-1-j)
     const int ybody = max(n * LDQ, tridiag_scratch_floats<QD, QD, SPLIT_NR2>());
-    int *pb = (int *)(sm + ybody);                   // fused: offset of the patch corner in the image
+    float *Bs = sm + ybody;                          // Bs[QD][PH]: the shared-memory part of the rows
+    int *pb = (int *)(Bs + QD * PH);                 // fused: offset of the patch corner in the image
     float *sv = sm;                                  // the tridiagonalisation's vectors re-use the head of Y
     const int rstride = P.pt * C * ps2;
     const long long HW = (long long)a.H * a.W, CHW = HW * C;
@@ -583,37 +614,57 @@ __global__ void __launch_bounds__(TT, 3) cov_tridiag_kernel(const BayesArgs a) {
     }
     __syncthreads();
     // ---- covariance, row t of B = C reversed, accumulated over the patches in order (bit-identical to bayes_kernel)
-    float2 b[2 * NCH];
+    const int tcol = min(tid, LDQ - 1);
+    const float live = tid < QD ? 1.f : 0.f;
+    float *bs_row = Bs + min(tid, QD - 1) * PH;
+    if constexpr (NSC > 0) {                         // first the columns that go to shared memory
+        float2 h[2 * (NSC > 0 ? NSC : 1)];
 #pragma unroll
-    for (int j = 0; j < 2 * NCH; ++j) b[j] = make_float2(0.f, 0.f);
-    float dg = 0.f;
-    {
-        const int tcol = min(tid, LDQ - 1);
-        const float live = tid < QD ? 1.f : 0.f;
+        for (int j = 0; j < 2 * NSC; ++j) h[j] = make_float2(0.f, 0.f);
         for (int nn = 0; nn < n; ++nn) {
             const float *row = Y + nn * LDQ;
             const float own = row[tcol] * live;
             const float2 od = make_float2(own, own);
-            dg = fmaf(own, own, dg);
 #pragma unroll
-            for (int jj = 0; jj < NCH; ++jj) {
-                const float4 f = *reinterpret_cast<const float4 *>(row + 4 * jj);
-                b[2 * jj] = __ffma2_rn(od, make_float2(f.x, f.y), b[2 * jj]);
-                b[2 * jj + 1] = __ffma2_rn(od, make_float2(f.z, f.w), b[2 * jj + 1]);
+            for (int jj = 0; jj < NSC; ++jj) {
+                const float4 f = *reinterpret_cast<const float4 *>(row + 4 * (NRC + jj));
+                h[2 * jj] = __ffma2_rn(od, make_float2(f.x, f.y), h[2 * jj]);
+                h[2 * jj + 1] = __ffma2_rn(od, make_float2(f.z, f.w), h[2 * jj + 1]);
             }
+        }
+        if (tid < QD) {
+#pragma unroll
+            for (int jj = 0; jj < NSC; ++jj)
+                reinterpret_cast<float4 *>(bs_row)[jj] = make_float4(h[2 * jj].x * inv_n, h[2 * jj].y * inv_n, h[2 * jj + 1].x * inv_n, h[2 * jj + 1].y * inv_n);
+        }
+    }
+    float2 b[2 * NRC];
+#pragma unroll
+    for (int j = 0; j < 2 * NRC; ++j) b[j] = make_float2(0.f, 0.f);
+    float dg = 0.f;
+    for (int nn = 0; nn < n; ++nn) {
+        const float *row = Y + nn * LDQ;
+        const float own = row[tcol] * live;
+        const float2 od = make_float2(own, own);
+        dg = fmaf(own, own, dg);
+#pragma unroll
+        for (int jj = 0; jj < NRC; ++jj) {
+            const float4 f = *reinterpret_cast<const float4 *>(row + 4 * jj);
+            b[2 * jj] = __ffma2_rn(od, make_float2(f.x, f.y), b[2 * jj]);
+            b[2 * jj + 1] = __ffma2_rn(od, make_float2(f.z, f.w), b[2 * jj + 1]);
         }
     }
 #pragma unroll
-    for (int j = 0; j < 2 * NCH; ++j) { b[j].x *= inv_n; b[j].y *= inv_n; }
+    for (int j = 0; j < 2 * NRC; ++j) { b[j].x *= inv_n; b[j].y *= inv_n; }
     __syncthreads();                                 // Y is dead
     if (a.rank_var) {                                // rank_var = mean over channels of trace(C) (bayes_est.py:39-40)
         float tr = warp_sum(dg * inv_n);
-        float *red = sm + ybody + ((n + 3) & ~3);
+        float *red = (float *)(pb + ((n + 3) & ~3));
         if (lane == 0) red[warp] = tr;
         __syncthreads();
         if (tid == 0) atomicAdd(&a.rank_var[g], ((red[0] + red[1]) + (red[2] + red[3])) / (float)C);
     }
-    tridiag_regs<QD, QD, SPLIT_NR2, TT>(b, sv, wsp, wsp + split_trail_off<QD>(), tid);
+    tridiag_regs<QD, QD, SPLIT_NR2, TT, NRC>(b, sv, wsp, wsp + split_trail_off<QD>(), tid, smem_u32(bs_row));
 }
 
 // Split path, second kernel: phase 2 of the tridiagonalisation on the NR x NR trailing matrix, 64 threads and
@@ -1478,8 +1529,12 @@ static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t 
         if (!a.ws) { set_error("%s: workspace of %zu bytes: %s", what, bytes, cudaGetErrorString(cudaGetLastError())); return VNLB_ERR_CUDA; }
         constexpr int scr1 = tridiag_scratch_floats<QD, QD, SPLIT_NR2>();
         const int ybody = a.L.n * 100 > scr1 ? a.L.n * 100 : scr1;
+        // Whole rows in registers (166 registers, 3 CTAs per SM).  The NRC < NCH variant of the kernel (64 columns in
+        // registers + the dying columns in shared memory, 128 registers, 4 CTAs per SM) measured 1.5 % SLOWER: this phase is
+        // bound by FFMA2 / LDS throughput, not by occupancy (profiles/r1_summary.md).
+        constexpr int NCHQ = (QD + 3) / 4;
         const size_t smem1 = (size_t)(ybody + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
-        auto k1 = cov_tridiag_kernel<FUSED, QD>;
+        auto k1 = cov_tridiag_kernel<FUSED, QD, NCHQ>;
         auto k1b = tridiag_tail_kernel<QD, SPLIT_NR2>;
         const size_t smem1b = (size_t)tridiag_scratch_floats<QD, SPLIT_NR2, 2>() * sizeof(float);
         auto k2 = bayes_kernel<FUSED, false, true>;
