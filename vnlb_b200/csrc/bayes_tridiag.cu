@@ -533,7 +533,7 @@ template <int QD> __host__ __device__ constexpr int split_ws_stride() { return s
 // the columns that survive this phase (<= 128 registers, 4 CTAs per SM).
 template <bool FUSED, int QD, int NRC>
 __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_kernel(const BayesArgs a) {
-    constexpr int LDQ = (QD + 3) & ~3, NCH = LDQ / 4, NSC = NCH - NRC, PH = 4 * NSC;   // NSC chunks per row in shared memory, pitch PH
+    constexpr int LDQ = (QD + 3) & ~3, NCH = LDQ / 4;
     extern __shared__ __align__(16) float sm[];
     const VnlbBayesParams &P = a.P;
     const int n = P.k, ps = P.ps, ps2 = ps * ps, C = P.c;
@@ -544,9 +544,8 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
     if (threadIdx.x == 0) wsp[3 * LDQ - 1] = valid_row ? 1.f : 0.f;   // flag for tridiag_tail_kernel
     if (!valid_row) return;
     float *Y = sm;                                   // Y[n][LDQ]: patches, columns reversed (column j = patch element QD-1-j)
-    const int ybody = max(n * LDQ, tridiag_scratch_floats<QD, QD, SPLIT_NR2>());
-    float *Bs = sm + ybody;                          // Bs[QD][PH]: the shared-memory part of the rows
-    int *pb = (int *)(Bs + QD * PH);                 // fused: offset of the patch corner in the image
+    const int ybody = max(max(n, LDQ) * LDQ, tridiag_scratch_floats<QD, QD, SPLIT_NR2>());   // patches, then the matrix, then the scratch
+    int *pb = (int *)(sm + ybody + 8);               // fused: offset of the patch corner in the image (8 floats of slack: tile reads)
     float *sv = sm;                                  // the tridiagonalisation's vectors re-use the head of Y
     const int rstride = P.pt * C * ps2;
     const long long HW = (long long)a.H * a.W, CHW = HW * C;
@@ -613,57 +612,89 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
         if (tid < QD) wsp[3 * LDQ + (QD - 1 - tid)] = mj; else wsp[3 * LDQ + tid] = 0.f;
     }
     __syncthreads();
-    // ---- covariance, row t of B = C reversed, accumulated over the patches in order (bit-identical to bayes_kernel)
-    const int tcol = min(tid, LDQ - 1);
-    const float live = tid < QD ? 1.f : 0.f;
-    float *bs_row = Bs + min(tid, QD - 1) * PH;
-    if constexpr (NSC > 0) {                         // first the columns that go to shared memory
-        float2 h[2 * (NSC > 0 ? NSC : 1)];
+    // ---- covariance: 8 x 8 register tiles of the lower triangle, accumulated over the patches in order (entries
+    //      bit-identical to bayes_kernel).  The kernel is bound by the shared-memory data pipe (ncu: 73-79 % busy), so the
+    //      covariance is formed where a loaded operand feeds most FMAs (4 LDS.128 per 32 FFMA2), then mirrored through
+    //      shared memory into the row-per-thread register layout of the tridiagonalisation.
+    static_assert(NRC == NCH, "cov_tridiag_kernel: rows fully in registers");
+    constexpr int NT8 = (LDQ + 7) / 8, NTRI = NT8 * (NT8 + 1) / 2;
+    static_assert(NTRI <= TT, "one 8 x 8 tile per thread");
+    int ti = -1, tj = 0;
+    if (tid < NTRI) {
+        ti = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
+        while (ti * (ti + 1) / 2 > tid) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
+        tj = tid - ti * (ti + 1) / 2;
+    }
+    {
+        float2 acc[8][4];
 #pragma unroll
-        for (int j = 0; j < 2 * NSC; ++j) h[j] = make_float2(0.f, 0.f);
-        for (int nn = 0; nn < n; ++nn) {
-            const float *row = Y + nn * LDQ;
-            const float own = row[tcol] * live;
-            const float2 od = make_float2(own, own);
+        for (int aa = 0; aa < 8; ++aa)
 #pragma unroll
-            for (int jj = 0; jj < NSC; ++jj) {
-                const float4 f = *reinterpret_cast<const float4 *>(row + 4 * (NRC + jj));
-                h[2 * jj] = __ffma2_rn(od, make_float2(f.x, f.y), h[2 * jj]);
-                h[2 * jj + 1] = __ffma2_rn(od, make_float2(f.z, f.w), h[2 * jj + 1]);
+            for (int bb = 0; bb < 4; ++bb) acc[aa][bb] = make_float2(0.f, 0.f);
+        if (ti >= 0) {
+            const float *ra = Y + 8 * ti, *rb = Y + 8 * tj;      // (columns >= LDQ of the last tile read the next row: never stored)
+            for (int nn = 0; nn < n; ++nn) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(ra + nn * LDQ), a1 = *reinterpret_cast<const float4 *>(ra + nn * LDQ + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(rb + nn * LDQ), b1 = *reinterpret_cast<const float4 *>(rb + nn * LDQ + 4);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float2 c0 = make_float2(b0.x, b0.y), c1 = make_float2(b0.z, b0.w), c2 = make_float2(b1.x, b1.y), c3 = make_float2(b1.z, b1.w);
+#pragma unroll
+                for (int aa = 0; aa < 8; ++aa) {
+                    const float2 ad = make_float2(av[aa], av[aa]);
+                    acc[aa][0] = __ffma2_rn(ad, c0, acc[aa][0]); acc[aa][1] = __ffma2_rn(ad, c1, acc[aa][1]);
+                    acc[aa][2] = __ffma2_rn(ad, c2, acc[aa][2]); acc[aa][3] = __ffma2_rn(ad, c3, acc[aa][3]);
+                }
             }
         }
-        if (tid < QD) {
+        __syncthreads();                             // Y is dead: its place takes the full symmetric matrix A[LDQ][LDQ]
+        if (ti >= 0) {
+            float *A = Y;
 #pragma unroll
-            for (int jj = 0; jj < NSC; ++jj)
-                reinterpret_cast<float4 *>(bs_row)[jj] = make_float4(h[2 * jj].x * inv_n, h[2 * jj].y * inv_n, h[2 * jj + 1].x * inv_n, h[2 * jj + 1].y * inv_n);
+            for (int aa = 0; aa < 8; ++aa) {         // rows 8 ti + aa, columns 8 tj .. 8 tj + 7
+                const int i = 8 * ti + aa;
+                if (i < LDQ) {
+                    *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
+                    if (8 * tj + 4 < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
+                }
+            }
+#pragma unroll
+            for (int bb = 0; bb < 8; ++bb) {         // mirrored: rows 8 tj + bb, columns 8 ti .. 8 ti + 7
+                const int j = 8 * tj + bb;
+                if (j < LDQ) {
+                    float cv[8];
+#pragma unroll
+                    for (int aa = 0; aa < 8; ++aa) cv[aa] = ((bb & 1) ? acc[aa][bb >> 1].y : acc[aa][bb >> 1].x) * inv_n;
+                    *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                    if (8 * ti + 4 < LDQ) *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+                }
+            }
         }
     }
-    float2 b[2 * NRC];
-#pragma unroll
-    for (int j = 0; j < 2 * NRC; ++j) b[j] = make_float2(0.f, 0.f);
+    __syncthreads();
+    float2 b[2 * NCH];                               // row t of B = C reversed
     float dg = 0.f;
-    for (int nn = 0; nn < n; ++nn) {
-        const float *row = Y + nn * LDQ;
-        const float own = row[tcol] * live;
-        const float2 od = make_float2(own, own);
-        dg = fmaf(own, own, dg);
+    {
+        const float *Ar = Y + min(tid, QD - 1) * LDQ;
+        const float live = tid < QD ? 1.f : 0.f;
 #pragma unroll
-        for (int jj = 0; jj < NRC; ++jj) {
-            const float4 f = *reinterpret_cast<const float4 *>(row + 4 * jj);
-            b[2 * jj] = __ffma2_rn(od, make_float2(f.x, f.y), b[2 * jj]);
-            b[2 * jj + 1] = __ffma2_rn(od, make_float2(f.z, f.w), b[2 * jj + 1]);
+        for (int jj = 0; jj < NCH; ++jj) {
+            const float4 f = *reinterpret_cast<const float4 *>(Ar + 4 * jj);
+            b[2 * jj] = make_float2(f.x * live, f.y * live);
+            b[2 * jj + 1] = make_float2(f.z * live, f.w * live);
         }
+        dg = Ar[min(tid, QD - 1)] * live;            // diagonal entry (already divided by n)
     }
-#pragma unroll
-    for (int j = 0; j < 2 * NRC; ++j) { b[j].x *= inv_n; b[j].y *= inv_n; }
-    __syncthreads();                                 // Y is dead
+    __syncthreads();                                 // A is dead
     if (a.rank_var) {                                // rank_var = mean over channels of trace(C) (bayes_est.py:39-40)
-        float tr = warp_sum(dg * inv_n);
+        float tr = warp_sum(dg);
         float *red = (float *)(pb + ((n + 3) & ~3));
         if (lane == 0) red[warp] = tr;
         __syncthreads();
         if (tid == 0) atomicAdd(&a.rank_var[g], ((red[0] + red[1]) + (red[2] + red[3])) / (float)C);
     }
+    float *bs_row = nullptr;
     tridiag_regs<QD, QD, SPLIT_NR2, TT, NRC>(b, sv, wsp, wsp + split_trail_off<QD>(), tid, smem_u32(bs_row));
 }
 
@@ -1528,12 +1559,13 @@ static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t 
         a.ws = split_workspace(bytes, st);
         if (!a.ws) { set_error("%s: workspace of %zu bytes: %s", what, bytes, cudaGetErrorString(cudaGetLastError())); return VNLB_ERR_CUDA; }
         constexpr int scr1 = tridiag_scratch_floats<QD, QD, SPLIT_NR2>();
-        const int ybody = a.L.n * 100 > scr1 ? a.L.n * 100 : scr1;
+        const int yrows = a.L.n > 100 ? a.L.n : 100;
+        const int ybody = yrows * 100 > scr1 ? yrows * 100 : scr1;
         // Whole rows in registers (166 registers, 3 CTAs per SM).  The NRC < NCH variant of the kernel (64 columns in
         // registers + the dying columns in shared memory, 128 registers, 4 CTAs per SM) measured 1.5 % SLOWER: this phase is
         // bound by FFMA2 / LDS throughput, not by occupancy (profiles/r1_summary.md).
         constexpr int NCHQ = (QD + 3) / 4;
-        const size_t smem1 = (size_t)(ybody + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
+        const size_t smem1 = (size_t)(ybody + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
         auto k1 = cov_tridiag_kernel<FUSED, QD, NCHQ>;
         auto k1b = tridiag_tail_kernel<QD, SPLIT_NR2>;
         const size_t smem1b = (size_t)tridiag_scratch_floats<QD, SPLIT_NR2, 2>() * sizeof(float);
