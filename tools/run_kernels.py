@@ -14,6 +14,8 @@ T, H, W = 16, 270, 480
 clean = synth.synth_video(T, H, W)
 noisy = torch.from_numpy(synth.add_noise(clean, 20.)).to(dev)
 yuv = color.rgb2yuv(noisy)
+# a realistic step-2 input: "basic" = clean + residual noise (sigma 3), not the noisy video itself
+yuv_basic = color.rgb2yuv(torch.from_numpy(synth.add_noise(clean, 3.)).to(dev))
 params = vnlb_b200.get_params(20.)
 for step in (0, 1):
     a = vnlb_b200.get_args(params, 3, step, dev)
@@ -26,14 +28,14 @@ for step in (0, 1):
     for it in range(2):
         ev[0].record()
         if which in ("search", "all"):
-            search.exec_sim_search_burst(yuv, q, vals, inds, None, 20., a)
+            search.exec_sim_search_burst(yuv if step == 0 else yuv_basic, q, vals, inds, None, 20., a)
         ev[1].record()
     if which == "search":
         torch.cuda.synchronize(); print("step", step, "search ms", ev[0].elapsed_time(ev[1]), "queries", q.shape[0]); continue
     if which in ("bayes", "fused"):
-        search.exec_sim_search_burst(yuv, q, vals, inds, None, 20., a)
+        search.exec_sim_search_burst(yuv if step == 0 else yuv_basic, q, vals, inds, None, 20., a)
     if which == "fused":
-        images = AttrDict(noisy=yuv, basic=yuv, deno=torch.zeros_like(yuv), weights=torch.zeros((T, H, W), device=dev))
+        images = AttrDict(noisy=yuv, basic=yuv if step == 0 else yuv_basic, deno=torch.zeros_like(yuv), weights=torch.zeros((T, H, W), device=dev))
         for it in range(2):
             ev[2].record()
             deno.bayes_aggregate_fused(images, inds, a)

@@ -135,6 +135,7 @@ struct BayesArgs {
     float *rank_var;
     float *ws;                     // split path: per-problem workspace (see cov_tridiag_kernel)
     int ws_stride;                 // floats per problem
+    int ws_pitch;                  // floats per (d | e | tau) vector in the workspace
     VnlbBayesParams P;
     TriLayout L;
 };
@@ -338,7 +339,7 @@ template <int QDG, int NR, int CEND> __host__ __device__ constexpr int tridiag_s
 
 // NRC = 4-column chunks of a row held in registers; chunks NRC .. NCH-1 (the columns that die first) live in this
 // thread's shared-memory row at byte address aBs: fewer registers => more CTAs per SM for the widest phase.
-template <int QDG, int NR, int CEND, int NT, int NRC = (NR + 3) / 4>
+template <int QDG, int NR, int CEND, int NT, int NRC = (NR + 3) / 4, int OPITCH = ((QDG + 3) & ~3), int OREFL = 4 * ((QDG + 3) & ~3)>
 __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * NRC], float *sv, float *out, float *trail, int tid, uint32_t aBs = 0) {
     constexpr int QD = NR;
     constexpr int LDQ = (QD + 3) & ~3;
@@ -516,10 +517,11 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * NRC], float *sv, fl
     const float *sd = sv + 6 * VL + 24;
     for (int idx = threadIdx.x; idx < NK; idx += NT) {
         out[K0 + idx] = sd[idx];
-        out[LDG + K0 + idx] = sd[KN + idx];
-        out[2 * LDG + K0 + idx] = sd[2 * KN + idx];
+        out[OPITCH + K0 + idx] = sd[KN + idx];
+        out[2 * OPITCH + K0 + idx] = sd[2 * KN + idx];
     }
-    for (int idx = threadIdx.x; idx < R1 - R0; idx += NT) out[4 * LDG + R0 + idx] = sd[3 * KN + idx];
+    for (int idx = threadIdx.x; idx < R1 - R0; idx += NT) out[OREFL + R0 + idx] = sd[3 * KN + idx];
+    (void)LDG;
 }
 
 // Workspace per problem (floats): d[LDG] e[LDG] tau[LDG] mean[LDG] reflectors[nref] trailing matrix[NR2 x NR2];
@@ -719,6 +721,179 @@ __global__ void __launch_bounds__(64, 8) tridiag_tail_kernel(const BayesArgs a) 
     tridiag_regs<QDG, NR, 2, 64>(b, sm, wsp, nullptr, tid);
 }
 
+
+// Split path of the Gram variant (step 2: n = 60 patches < p = 98 elements): centre + Gram matrix G = Yc Yc^T / n +
+// its whole tridiagonalisation, one CTA of 64 threads per (group, channel) problem, 8 CTAs per SM.  Same structure as
+// cov_tridiag_kernel with the roles of patches and patch elements swapped: the patches are staged TRANSPOSED,
+// Yt[j][t] = element j of patch QD-1-t, so that thread t ends up with row t of the reversed Gram matrix.
+// Workspace per problem (floats): d[64] e[64] tau[64] (tau[63] = valid flag) mean[LD] reflectors[nref].
+constexpr int GRAM_PITCH = 64;
+template <int QD> __host__ __device__ constexpr int gram_ws_stride(int LD) { return 3 * GRAM_PITCH + LD + ((((QD - 1) * QD / 2) + 3) & ~3); }
+
+template <bool FUSED, int QD>
+__global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) {
+    constexpr int NT = 64, LDQ = (QD + 3) & ~3, NCH = LDQ / 4;
+    static_assert(QD <= 64 && QD % 4 == 0, "gram_tridiag_kernel: one row per thread of 2 warps");
+    extern __shared__ __align__(16) float sm[];
+    const VnlbBayesParams &P = a.P;
+    const TriLayout &L = a.L;
+    const int n = P.k, ps = P.ps, ps2 = ps * ps, C = P.c, p = L.p, LD = L.LD;
+    const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + warp_rotation()) & 1, tid = 32 * warp + lane;
+    const int g = blockIdx.x / C, ch = blockIdx.x - g * C;
+    float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
+    const bool valid_row = !a.inds || row_valid_block(a.inds + (long long)g * n, n);
+    if (threadIdx.x == 0) wsp[3 * GRAM_PITCH - 1] = valid_row ? 1.f : 0.f;
+    if (!valid_row) return;
+    // shared memory: Yt[p][LDQ] (+8 floats of slack for the tile reads), later A[LDQ][LDQ] and the scratch of tridiag_regs; pb[n]
+    const int ybody = max(max(p * LDQ, LDQ * LDQ), tridiag_scratch_floats<QD, QD, 2>());
+    float *Yt = sm;
+    int *pb = (int *)(sm + ybody + 8);
+    const int rstride = P.pt * C * ps2;
+    const long long HW = (long long)a.H * a.W, CHW = HW * C;
+    if (FUSED) {
+        int bad = 0;
+        for (int nn = tid; nn < n; nn += NT) {
+            int t, y, x;
+            decode_ind(a.inds[(long long)g * n + nn], a.H, a.W, C, t, y, x);
+            bad |= (t < 0 || t + P.pt > a.T || y + ps > a.H || x + ps > a.W);
+            pb[nn] = (int)((long long)t * CHW + (long long)y * a.W + x);
+        }
+        if (__syncthreads_or(bad)) {
+            if (threadIdx.x == 0) wsp[3 * GRAM_PITCH - 1] = 0.f;
+            return;
+        }
+    }
+    auto col_off = [&](int j) -> int {
+        const int dt = j / ps2, r = j - dt * ps2;
+        if (FUSED) { const int dy = r / ps, dx = r - dy * ps; return (int)(dt * CHW + ch * HW + (long long)dy * a.W + dx); }
+        return (dt * C + ch) * ps2 + r;
+    };
+    const float *src = FUSED ? (P.cov_from_basic ? a.img_basic : a.img_noisy)
+                             : (P.cov_from_basic ? a.pbasic : a.pnoisy) + (long long)g * n * rstride;
+    int co[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) co[q] = col_off(min(lane + 32 * q, p - 1));
+    // ---- stage the patches transposed and reversed: Yt[j][QD-1-nn] = patch nn, element j (5 patches in flight per warp)
+    constexpr int SU = 5;
+    for (int n0 = warp; n0 < LDQ; n0 += SU * (NT / 32)) {
+        float vals[SU][4];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int nn = min(n0 + u * (NT / 32), n - 1);
+            const float *q = src + (FUSED ? (long long)pb[nn] : (long long)nn * rstride);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) vals[u][qq] = q[co[qq]];
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int nn = n0 + u * (NT / 32);
+            if (nn < LDQ) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int j = lane + 32 * qq;
+                    if (j < p) Yt[j * LDQ + (LDQ - 1 - nn)] = nn < n ? vals[u][qq] : 0.f;   // patches n..LDQ-1: zero pad (n == QD == LDQ here)
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- centre every patch element (same summation order as bayes_kernel: 4 interleaved partial sums over the patches)
+    const float inv_n = 1.f / (float)n;
+    for (int j = tid; j < LD; j += NT) {
+        float mj = 0.f;
+        if (j < p) {
+            float *row = Yt + j * LDQ + (LDQ - 1);          // patch nn at row[-nn]
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int nn = 0;
+            for (; nn + 3 < n; nn += 4) { s0 += row[-nn]; s1 += row[-(nn + 1)]; s2 += row[-(nn + 2)]; s3 += row[-(nn + 3)]; }
+            for (; nn < n; ++nn) s0 += row[-nn];
+            mj = ((s0 + s1) + (s2 + s3)) * inv_n;
+            for (nn = 0; nn < n; ++nn) row[-nn] -= mj;
+        }
+        wsp[3 * GRAM_PITCH + j] = mj;
+    }
+    __syncthreads();
+    // ---- Gram matrix in 8 x 8 register tiles of the lower triangle (one tile per thread), summed over the elements in order
+    constexpr int NT8 = (LDQ + 7) / 8, NTRI = NT8 * (NT8 + 1) / 2;
+    static_assert(NTRI <= NT, "one 8 x 8 tile per thread");
+    int ti = -1, tj = 0;
+    if (tid < NTRI) {
+        ti = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
+        while (ti * (ti + 1) / 2 > tid) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
+        tj = tid - ti * (ti + 1) / 2;
+    }
+    {
+        float2 acc[8][4];
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) acc[aa][bb] = make_float2(0.f, 0.f);
+        if (ti >= 0) {
+            const float *ra = Yt + 8 * ti, *rb = Yt + 8 * tj;
+            for (int j = 0; j < p; ++j) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(ra + j * LDQ), a1 = *reinterpret_cast<const float4 *>(ra + j * LDQ + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(rb + j * LDQ), b1 = *reinterpret_cast<const float4 *>(rb + j * LDQ + 4);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float2 c0 = make_float2(b0.x, b0.y), c1 = make_float2(b0.z, b0.w), c2 = make_float2(b1.x, b1.y), c3 = make_float2(b1.z, b1.w);
+#pragma unroll
+                for (int aa = 0; aa < 8; ++aa) {
+                    const float2 ad = make_float2(av[aa], av[aa]);
+                    acc[aa][0] = __ffma2_rn(ad, c0, acc[aa][0]); acc[aa][1] = __ffma2_rn(ad, c1, acc[aa][1]);
+                    acc[aa][2] = __ffma2_rn(ad, c2, acc[aa][2]); acc[aa][3] = __ffma2_rn(ad, c3, acc[aa][3]);
+                }
+            }
+        }
+        __syncthreads();                             // Yt is dead: its place takes the full symmetric matrix A[LDQ][LDQ]
+        if (ti >= 0) {
+            float *A = Yt;
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) {
+                const int i = 8 * ti + aa;
+                if (i < LDQ) {
+                    *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
+                    if (8 * tj + 4 < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
+                }
+            }
+#pragma unroll
+            for (int bb = 0; bb < 8; ++bb) {
+                const int j = 8 * tj + bb;
+                if (j < LDQ) {
+                    float cv[8];
+#pragma unroll
+                    for (int aa = 0; aa < 8; ++aa) cv[aa] = ((bb & 1) ? acc[aa][bb >> 1].y : acc[aa][bb >> 1].x) * inv_n;
+                    *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                    if (8 * ti + 4 < LDQ) *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float2 b[2 * NCH];
+    float dg;
+    {
+        const float *Ar = Yt + min(tid, QD - 1) * LDQ;
+        const float live = tid < QD ? 1.f : 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NCH; ++jj) {
+            const float4 f = *reinterpret_cast<const float4 *>(Ar + 4 * jj);
+            b[2 * jj] = make_float2(f.x * live, f.y * live);
+            b[2 * jj + 1] = make_float2(f.z * live, f.w * live);
+        }
+        dg = Ar[min(tid, QD - 1)] * live;
+    }
+    __syncthreads();                                 // A is dead
+    if (a.rank_var) {                                // rank_var = mean over channels of trace(C) = trace(G) (bayes_est.py:39-40)
+        float tr = warp_sum(dg);
+        float *red = (float *)(pb + ((n + 3) & ~3));
+        if (lane == 0) red[warp] = tr;
+        __syncthreads();
+        if (tid == 0) atomicAdd(&a.rank_var[g], (red[0] + red[1]) / (float)C);
+    }
+    tridiag_regs<QD, QD, 2, NT, NCH, GRAM_PITCH, 3 * GRAM_PITCH + 100>(b, sm, wsp, nullptr, tid);
+}
+
 // SPLIT: phases 0-1 were done by cov_tridiag_kernel; (d, e, tau, mean, packed reflectors) come from the workspace.
 template <bool FUSED, bool GRAM, bool SPLIT>
 __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs a) {
@@ -807,15 +982,16 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
         if constexpr (SPLIT) {
             // (d, e, tau, mean | packed reflectors) of problem (g, ch), written by cov_tridiag_kernel
             const float4 *wsp = reinterpret_cast<const float4 *>(a.ws + (size_t)(g * C + ch) * a.ws_stride);
-            const int nhead = LDq;                      // 4 vectors of LDq floats = LDq float4
-            for (int idx = tid; idx < nhead; idx += TT) {
+            const int pitch4 = a.ws_pitch >> 2;         // d, e, tau: `ws_pitch` floats each; then mean[LD]; then the reflectors
+            for (int idx = tid; idx < 3 * pitch4; idx += TT) {
                 const float4 f = wsp[idx];
-                const int which = idx / (LDq >> 2), off = 4 * (idx - which * (LDq >> 2));
-                float *dst = which == 0 ? d : (which == 1 ? e : (which == 2 ? taus : mean));
+                const int which = idx / pitch4, off = 4 * (idx - which * pitch4);
+                float *dst = which == 0 ? d : (which == 1 ? e : taus);
                 *reinterpret_cast<float4 *>(dst + off) = f;
             }
+            for (int idx = tid; idx < (LD >> 2); idx += TT) reinterpret_cast<float4 *>(mean)[idx] = wsp[3 * pitch4 + idx];
             const int nref4 = (((qd - 1) * qd / 2 + 3) & ~3) >> 2;
-            for (int idx = tid; idx < nref4; idx += TT) reinterpret_cast<float4 *>(R)[idx] = wsp[nhead + idx];
+            for (int idx = tid; idx < nref4; idx += TT) reinterpret_cast<float4 *>(R)[idx] = wsp[3 * pitch4 + (LD >> 2) + idx];
             __syncthreads();
         } else {
         // -------------------------------------------------------------- 0. centre + covariance
@@ -1506,7 +1682,9 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
 static int g_split = -1;   // -1: not read yet; VNLB_BAYES_SPLIT=0 in the environment or vnlb_set_bayes_split(0) disables
 static bool use_split(const TriLayout &L) {
     if (g_split < 0) { const char *s = getenv("VNLB_BAYES_SPLIT"); g_split = (s && s[0] == '0') ? 0 : 1; }
-    return g_split != 0 && !L.gram && L.q == 98 && (size_t)(L.n * 100 + L.n + 16) * sizeof(float) <= 72 * 1024;
+    if (g_split == 0) return false;
+    if (!L.gram) return L.q == 98 && (size_t)(L.n * 100 + L.n + 16) * sizeof(float) <= 72 * 1024;   // step 1: 7x7x2, direct covariance
+    return L.q == 60 && L.n == 60 && L.p == 98;                                                       // step 2: 7x7x2, k = 60, Gram trick
 }
 int set_bayes_split(int on) {
     const int prev = g_split < 0 ? 1 : g_split;
@@ -1550,8 +1728,30 @@ template <bool FUSED>
 static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t st) {
     const VnlbBayesParams *p = &a.P;
     cudaError_t e;
+    if (use_split(a.L) && a.L.gram) {
+        constexpr int QD = 60;
+        a.ws_pitch = GRAM_PITCH;
+        a.ws_stride = gram_ws_stride<QD>(a.L.LD);
+        const size_t bytes = (size_t)B * p->c * a.ws_stride * sizeof(float);
+        a.ws = split_workspace(bytes, st);
+        if (!a.ws) { set_error("%s: workspace of %zu bytes: %s", what, bytes, cudaGetErrorString(cudaGetLastError())); return VNLB_ERR_CUDA; }
+        const size_t smem = (size_t)a.L.total * sizeof(float);
+        constexpr int scr = tridiag_scratch_floats<QD, QD, 2>();
+        int ybody = a.L.p * QD > QD * QD ? a.L.p * QD : QD * QD;
+        if (ybody < scr) ybody = scr;
+        const size_t smem1 = (size_t)(ybody + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
+        auto k1 = gram_tridiag_kernel<FUSED, QD>;
+        auto k2 = bayes_kernel<FUSED, true, true>;
+        e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
+        k1<<<B * p->c, 64, smem1, st>>>(a);
+        k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
+        return check_launch(what, 2);
+    }
     if (use_split(a.L)) {
         a.L = tri_layout(a.L.n, a.L.p, true);            // no covariance matrix in the eigen/filter kernel
+        a.ws_pitch = 100;
         const size_t smem = (size_t)a.L.total * sizeof(float);
         constexpr int QD = 98;
         a.ws_stride = split_ws_stride<QD>();
