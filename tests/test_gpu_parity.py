@@ -461,6 +461,52 @@ def test_bayes_split_path_matches_single_kernel_and_oracle(vb, kind):
     assert np.abs(outs[1][0] - outs[0][0]).max() <= 2e-4 * scale
 
 
+@pytest.mark.parametrize("kind", ["texture", "flatmix", "duplicates"])
+def test_bayes_gram_split_path_matches_single_kernel_and_oracle(vb, kind):
+    """Step-2 production shape (7x7x2, k = 60, covariance from the basic patches, Gram trick): the split path
+    (gram_tridiag_kernel + eigen/filter kernel) == the single kernel == the oracle."""
+    from vnlb_b200 import _lib, deno
+    from vnlb_b200.utils import AttrDict
+    a_gpu, a_cpu = gargs(vb, 1), oargs(1)
+    rs = np.random.RandomState(17)
+    B, k = 20, a_cpu.npatches
+    shape = (B, k, 2, 3, 7, 7)
+    if kind == "texture":
+        proto = rs.rand(B, 6, 2, 3, 7, 7).astype(np.float32) * 255
+        mix = rs.rand(B, k, 6).astype(np.float32)
+        pb = np.einsum("bkr,brtchw->bktchw", mix, proto).astype(np.float32)
+    elif kind == "flatmix":                       # half of the groups are flat (variance below gamma * sigma^2)
+        pb = np.full(shape, 80., np.float32) + rs.randn(*shape).astype(np.float32) * 0.5
+        pb[::2] += rs.rand(B // 2, k, 2, 3, 7, 7).astype(np.float32) * 120
+    else:
+        half = (rs.rand(B, k // 2, 2, 3, 7, 7) * 255).astype(np.float32)
+        pb = np.concatenate([half, half], 1)
+    pn = pb + rs.randn(*shape).astype(np.float32) * 20
+    if kind == "flatmix":
+        pn[1::2] = pb[1::2] + rs.randn(B // 2, k, 2, 3, 7, 7).astype(np.float32) * 6      # variance 36 < gamma * sigma^2 = 80: flat groups
+    flat = orc.exec_flat_areas(pn, a_cpu.gamma, a_cpu.sigma2)
+    if kind == "flatmix":
+        assert flat.any() and not flat.all()
+    ref, _, _ = orc.bayes_denoise(pn.copy(), pb.copy(), flat, a_cpu)
+    outs = {}
+    for split in (1, 0):
+        prev = _lib.lib.vnlb_set_bayes_split(split)
+        try:
+            patches = AttrDict(noisy=cu(pn.copy()), basic=cu(pb.copy()), flat=cu(flat.astype(np.uint8)))
+            rv = deno.denoise(patches, a_gpu, "bayes", None)
+            outs[split] = (patches.noisy.cpu().numpy(), rv.cpu().numpy())
+        finally:
+            _lib.lib.vnlb_set_bayes_split(prev)
+    for split in (1, 0):
+        out, rv = outs[split]
+        assert np.isfinite(out).all(), (kind, split)
+        for b in range(B):
+            den = max(np.linalg.norm(ref[b]), 1e-20)
+            assert np.linalg.norm(out[b] - ref[b]) / den < 1e-4, (kind, split, b)
+    np.testing.assert_allclose(outs[1][1], outs[0][1], rtol=1e-6)
+    assert np.abs(outs[1][0] - outs[0][0]).max() <= 2e-4 * np.abs(outs[0][0]).max()
+
+
 def test_e2e_fast_schedule_psnr(vb, golden_dir):
     """The throughput schedule (fused and staged) stays within the PSNR band of the parity run."""
     g = np.load(os.path.join(golden_dir, "e2e.npz"))
