@@ -528,7 +528,9 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * NRC], float *sv, fl
 // tau[LDG-1] doubles as the "problem is valid" flag between the kernels of the split path.
 constexpr int SPLIT_NR2 = 64;                      // trailing size handed from phase 1 to phase 2
 template <int QD> __host__ __device__ constexpr int split_trail_off() { return 4 * ((QD + 3) & ~3) + ((((QD - 1) * QD / 2) + 3) & ~3); }
-template <int QD> __host__ __device__ constexpr int split_ws_stride() { return split_trail_off<QD>() + SPLIT_NR2 * SPLIT_NR2; }
+constexpr int SPLIT_NR3 = 32;                      // trailing size handed from phase 2 to phase 3
+template <int QD> __host__ __device__ constexpr int split_trail2_off() { return split_trail_off<QD>() + SPLIT_NR2 * SPLIT_NR2; }
+template <int QD> __host__ __device__ constexpr int split_ws_stride() { return split_trail2_off<QD>() + SPLIT_NR3 * SPLIT_NR3; }
 
 // NRC: 4-column chunks of a row kept in registers (the rest of the row lives in shared memory until those columns are
 // eliminated): NRC = NCH is everything in registers (166 registers, 3 CTAs per SM), NRC = SPLIT_NR2 / 4 keeps exactly
@@ -700,17 +702,19 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
     tridiag_regs<QD, QD, SPLIT_NR2, TT, NRC>(b, sv, wsp, wsp + split_trail_off<QD>(), tid, smem_u32(bs_row));
 }
 
-// Split path, second kernel: phase 2 of the tridiagonalisation on the NR x NR trailing matrix, 64 threads and
-// ~110 registers => 8 CTAs per SM for the 62 short, latency-bound steps that remain.
-template <int QDG, int NR>
-__global__ void __launch_bounds__(64, 8) tridiag_tail_kernel(const BayesArgs a) {
-    constexpr int LDG = (QDG + 3) & ~3, NCH = NR / 4;
-    static_assert(NR % 4 == 0 && NR <= 64, "tridiag_tail_kernel: one row per thread of 2 warps");
+// Split path, later phases of the tridiagonalisation: the NR x NR trailing matrix comes from the workspace (float
+// offset TIN, row pitch NR), columns NR-1 .. CEND are eliminated by NT = round32(NR) threads, and unless CEND == 2 the
+// CEND x CEND rest goes back to the workspace at TOUT.  Registers ~ NR + 62: 64 threads x 126 registers => 8 CTAs per SM
+// for NR = 64, 32 threads x 94 => 16+ CTAs per SM for NR = 32 -- occupancy follows the shrinking problem.
+template <int QDG, int NR, int CEND, int NT, int OCC, int OPITCH, int OREFL, int TIN, int TOUT>
+__global__ void __launch_bounds__(NT, OCC) tridiag_tail_kernel(const BayesArgs a) {
+    constexpr int NCH = NR / 4;
+    static_assert(NR % 4 == 0 && NR <= NT && NT % 32 == 0 && NT <= 64, "tridiag_tail_kernel: one row per thread, at most 2 warps");
     extern __shared__ __align__(16) float sm[];
     float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
-    if (wsp[3 * LDG - 1] == 0.f) return;              // group skipped by cov_tridiag_kernel
-    const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + warp_rotation()) & 1, tid = 32 * warp + lane;
-    const float4 *tr = reinterpret_cast<const float4 *>(wsp + split_trail_off<QDG>() + min(tid, NR - 1) * NR);
+    if (wsp[3 * OPITCH - 1] == 0.f) return;           // group skipped by the first kernel
+    const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + warp_rotation()) & (NT / 32 - 1), tid = 32 * warp + lane;
+    const float4 *tr = reinterpret_cast<const float4 *>(wsp + TIN + min(tid, NR - 1) * NR);
     float2 b[2 * NCH];
 #pragma unroll
     for (int I = 0; I < NCH; ++I) {
@@ -718,7 +722,7 @@ __global__ void __launch_bounds__(64, 8) tridiag_tail_kernel(const BayesArgs a) 
         b[2 * I] = make_float2(f.x, f.y);
         b[2 * I + 1] = make_float2(f.z, f.w);
     }
-    tridiag_regs<QDG, NR, 2, 64>(b, sm, wsp, nullptr, tid);
+    tridiag_regs<QDG, NR, CEND, NT, NCH, OPITCH, OREFL>(b, sm, wsp, wsp + TOUT, tid);
 }
 
 
@@ -728,7 +732,8 @@ __global__ void __launch_bounds__(64, 8) tridiag_tail_kernel(const BayesArgs a) 
 // Yt[j][t] = element j of patch QD-1-t, so that thread t ends up with row t of the reversed Gram matrix.
 // Workspace per problem (floats): d[64] e[64] tau[64] (tau[63] = valid flag) mean[LD] reflectors[nref].
 constexpr int GRAM_PITCH = 64;
-template <int QD> __host__ __device__ constexpr int gram_ws_stride(int LD) { return 3 * GRAM_PITCH + LD + ((((QD - 1) * QD / 2) + 3) & ~3); }
+template <int QD> __host__ __device__ constexpr int gram_trail_off(int LD) { return 3 * GRAM_PITCH + LD + ((((QD - 1) * QD / 2) + 3) & ~3); }
+template <int QD> __host__ __device__ constexpr int gram_ws_stride(int LD) { return gram_trail_off<QD>(LD) + SPLIT_NR3 * SPLIT_NR3; }
 
 template <bool FUSED, int QD>
 __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) {
@@ -745,7 +750,7 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
     if (threadIdx.x == 0) wsp[3 * GRAM_PITCH - 1] = valid_row ? 1.f : 0.f;
     if (!valid_row) return;
     // shared memory: Yt[p][LDQ] (+8 floats of slack for the tile reads), later A[LDQ][LDQ] and the scratch of tridiag_regs; pb[n]
-    const int ybody = max(max(p * LDQ, LDQ * LDQ), tridiag_scratch_floats<QD, QD, 2>());
+    const int ybody = max(max(p * LDQ, LDQ * LDQ), tridiag_scratch_floats<QD, QD, SPLIT_NR3>());
     float *Yt = sm;
     int *pb = (int *)(sm + ybody + 8);
     const int rstride = P.pt * C * ps2;
@@ -891,7 +896,7 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
         __syncthreads();
         if (tid == 0) atomicAdd(&a.rank_var[g], (red[0] + red[1]) / (float)C);
     }
-    tridiag_regs<QD, QD, 2, NT, NCH, GRAM_PITCH, 3 * GRAM_PITCH + 100>(b, sm, wsp, nullptr, tid);
+    tridiag_regs<QD, QD, SPLIT_NR3, NT, NCH, GRAM_PITCH, 3 * GRAM_PITCH + 100>(b, sm, wsp, wsp + gram_trail_off<QD>(100), tid);   // columns QD-1 .. 32; the rest in tridiag_tail_kernel
 }
 
 // SPLIT: phases 0-1 were done by cov_tridiag_kernel; (d, e, tau, mean, packed reflectors) come from the workspace.
@@ -1736,18 +1741,21 @@ static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t 
         a.ws = split_workspace(bytes, st);
         if (!a.ws) { set_error("%s: workspace of %zu bytes: %s", what, bytes, cudaGetErrorString(cudaGetLastError())); return VNLB_ERR_CUDA; }
         const size_t smem = (size_t)a.L.total * sizeof(float);
-        constexpr int scr = tridiag_scratch_floats<QD, QD, 2>();
+        constexpr int scr = tridiag_scratch_floats<QD, QD, SPLIT_NR3>();
         int ybody = a.L.p * QD > QD * QD ? a.L.p * QD : QD * QD;
         if (ybody < scr) ybody = scr;
         const size_t smem1 = (size_t)(ybody + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
         auto k1 = gram_tridiag_kernel<FUSED, QD>;
+        auto k1c = tridiag_tail_kernel<QD, SPLIT_NR3, 2, 32, 16, GRAM_PITCH, 3 * GRAM_PITCH + 100, gram_trail_off<QD>(100), 0>;
+        const size_t smem1c = (size_t)tridiag_scratch_floats<QD, SPLIT_NR3, 2>() * sizeof(float);
         auto k2 = bayes_kernel<FUSED, true, true>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
         k1<<<B * p->c, 64, smem1, st>>>(a);
+        k1c<<<B * p->c, 32, smem1c, st>>>(a);
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
-        return check_launch(what, 2);
+        return check_launch(what, 3);
     }
     if (use_split(a.L)) {
         a.L = tri_layout(a.L.n, a.L.p, true);            // no covariance matrix in the eigen/filter kernel
@@ -1767,16 +1775,20 @@ static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t 
         constexpr int NCHQ = (QD + 3) / 4;
         const size_t smem1 = (size_t)(ybody + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
         auto k1 = cov_tridiag_kernel<FUSED, QD, NCHQ>;
-        auto k1b = tridiag_tail_kernel<QD, SPLIT_NR2>;
-        const size_t smem1b = (size_t)tridiag_scratch_floats<QD, SPLIT_NR2, 2>() * sizeof(float);
+        constexpr int LDG = (QD + 3) & ~3;
+        auto k1b = tridiag_tail_kernel<QD, SPLIT_NR2, SPLIT_NR3, 64, 8, LDG, 4 * LDG, split_trail_off<QD>(), split_trail2_off<QD>()>;
+        auto k1c = tridiag_tail_kernel<QD, SPLIT_NR3, 2, 32, 16, LDG, 4 * LDG, split_trail2_off<QD>(), 0>;
+        const size_t smem1b = (size_t)tridiag_scratch_floats<QD, SPLIT_NR2, SPLIT_NR3>() * sizeof(float);
+        const size_t smem1c = (size_t)tridiag_scratch_floats<QD, SPLIT_NR3, 2>() * sizeof(float);
         auto k2 = bayes_kernel<FUSED, false, true>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
         k1<<<B * p->c, TT, smem1, st>>>(a);
         k1b<<<B * p->c, 64, smem1b, st>>>(a);
+        k1c<<<B * p->c, 32, smem1c, st>>>(a);
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
-        return check_launch(what, 3);
+        return check_launch(what, 4);
     }
     const size_t smem = (size_t)a.L.total * sizeof(float);
     auto kern = a.L.gram ? bayes_kernel<FUSED, true, false> : bayes_kernel<FUSED, false, false>;
