@@ -47,7 +47,7 @@ struct TriLayout {
     int gram;                      // 1: eigen-decompose the n x n Gram matrix Y Y^T/n instead of the p x p covariance
     int q, LDq, ZSq;               // dimension of the eigenproblem and its pitches
     int oR, rsize, oZ, oVt, oX, xrows;  // inside R: packed reflectors at 0, Z at oZ; later (Ut at 0,) Vt at oVt, X at oX
-    int oD, oE, oE2, oTau, oV, oW, oMean, oLam, oCoef, oLo, oHi, oNlo, oNhi, oRed, oT, oPb, total;
+    int oD, oE, oE2, oTau, oV, oW, oMean, oLam, oCoef, oLo, oHi, oNlo, oNhi, oRed, oT, oCnt, oPb, total;
 };
 
 static TriLayout tri_layout(int n, int p, bool split = false) {
@@ -113,6 +113,7 @@ static TriLayout tri_layout(int n, int p, bool split = false) {
     L.oRed = o; o += 16;
     L.oT = o; o += 10 * ((vlen + 3) / 4) + 2;               // compact-WY factors of the back-transformation: 10 floats per block of 4 reflectors
     o = (o + 3) & ~3;
+    L.oCnt = o; o += TT;                                     // Sturm counts of the 128 section points of round 0
     L.oPb = o; o += 2 * ((n + 3) & ~3);                     // fused mode: per-patch image / weight offsets
     L.total = o;
     return L;
@@ -1245,63 +1246,83 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
         const float tau_eff = fmaf(P.thresh, P.sigma2, P.sigmab2);   // eigenvalue > tau_eff <=> coefficient != 0
         const float gmax = gmax0 + 1e-6f * fabsf(gmax0) + pivmin;
 
-        int m;  // eigenpairs to compute
-        {       // one Sturm count at the threshold: #eigenvalues < tau_eff
+        // Sturm count #eigenvalues < x of the tridiagonal matrix, 4 pivots per pair of LDS.128
+        auto sturm_count = [&](float x) -> int {
             float q = 1.f;
             int cnt = 0;
-            for (int j = 0; j < qd; ++j) {
-                float t = (d[j] - tau_eff) - __fdividef(e2[j], q);
+            int j = 0;
+            for (; j + 3 < qd; j += 4) {
+                const float4 d4 = *reinterpret_cast<const float4 *>(d + j), e4 = *reinterpret_cast<const float4 *>(e2 + j);
+                float t = (d4.x - x) - __fdividef(e4.x, q);
+                if (fabsf(t) < pivmin) t = -pivmin;
+                cnt += t < 0.f;
+                float u = (d4.y - x) - __fdividef(e4.y, t);
+                if (fabsf(u) < pivmin) u = -pivmin;
+                cnt += u < 0.f;
+                t = (d4.z - x) - __fdividef(e4.z, u);
+                if (fabsf(t) < pivmin) t = -pivmin;
+                cnt += t < 0.f;
+                q = (d4.w - x) - __fdividef(e4.w, t);
+                if (fabsf(q) < pivmin) q = -pivmin;
+                cnt += q < 0.f;
+            }
+            for (; j < qd; ++j) {
+                float t = (d[j] - x) - __fdividef(e2[j], q);
                 if (fabsf(t) < pivmin) t = -pivmin;
                 q = t;
                 cnt += t < 0.f;
             }
-            m = min(qd - cnt, P.rank);
+            return cnt;
+        };
+        // Round 0: 128 DISTINCT section points over [tau_eff, gmax] (thread 0 sits exactly on the threshold), one Sturm chain
+        // each: the count at the threshold gives the number m of eigenpairs to compute, the other counts bracket every one
+        // of them to 1/128 of the interval at once.
+        int m;
+        int *scnt = (int *)(sm + L.oCnt);
+        {
+            const float x0 = fmaf(gmax - tau_eff, (float)tid / (float)TT, tau_eff);
+            scnt[tid] = sturm_count(x0);
+            __syncthreads();
+            m = min(qd - scnt[0], P.rank);
             if (gmax <= tau_eff) m = 0;
         }
         float *Z = R + L.oZ;
         if (m > 0) {
-            for (int j = tid; j < m; j += TT) { blo[j] = tau_eff; bhi[j] = gmax; }
+            if (tid < m) {
+                const int idx = qd - 1 - tid;               // ascending index of the tid-th largest eigenvalue
+                int tlo = 0, thi = TT;
+                for (int t = 0; t < TT; ++t) {
+                    const int c = scnt[t];
+                    if (c <= idx) tlo = max(tlo, t); else thi = min(thi, t);
+                }
+                blo[tid] = fmaf(gmax - tau_eff, (float)tlo / (float)TT, tau_eff);
+                bhi[tid] = thi < TT ? fmaf(gmax - tau_eff, (float)thi / (float)TT, tau_eff) : gmax;
+                if (blo[tid] > bhi[tid]) { const float mid = 0.5f * (blo[tid] + bhi[tid]); blo[tid] = mid; bhi[tid] = mid; }
+            }
             __syncthreads();
             const int G = (TT * ILP) / m;                 // section points per eigenvalue and round
-            int rounds = 1;
-            { float res = (float)(G + 1); while (res < 1.7e7f && rounds < 14) { res *= (float)(G + 1); ++rounds; } }  // 2^24 sections
+            int rounds = 0;
+            { float res = (float)TT; while (res < 1.7e7f && rounds < 14) { res *= (float)(G + 1); ++rounds; } }  // 2^24 sections in all
             for (int r = 0; r < rounds; ++r) {
                 for (int j = tid; j < m; j += TT) { nlo[j] = __float_as_int(blo[j]); nhi[j] = __float_as_int(bhi[j]); }
                 __syncthreads();
-                float x[ILP], q[ILP];
-                int ej[ILP], cnt[ILP];
-#pragma unroll
-                for (int c = 0; c < ILP; ++c) {
-                    const int pt = tid * ILP + c;
-                    const int j = pt / G, qi = pt - j * G;
-                    ej[c] = j < m ? j : -1;
-                    const float lo = blo[min(j, m - 1)], hi = bhi[min(j, m - 1)];
-                    x[c] = fmaf(hi - lo, (float)(qi + 1) / (float)(G + 1), lo);
-                    q[c] = 1.f;
-                    cnt[c] = 0;
+                static_assert(ILP == 1, "one Sturm chain per thread");
+                const int pt = tid;
+                const int j = pt / G, qi = pt - j * G;
+                const int ej = j < m ? j : -1;
+                const float lo = blo[min(j, m - 1)], hi = bhi[min(j, m - 1)];
+                const float x = fmaf(hi - lo, (float)(qi + 1) / (float)(G + 1), lo);
+                const int cnt = sturm_count(x);
+                if (ej >= 0) {
+                    const int idx = qd - 1 - ej;          // ascending index of the ej-th largest eigenvalue
+                    if (cnt <= idx) atomicMax(&nlo[ej], __float_as_int(x));   // x is a lower bound
+                    else atomicMin(&nhi[ej], __float_as_int(x));              // x is an upper bound
                 }
-                for (int j = 0; j < qd; ++j) {             // 4 interleaved Sturm chains: #eigenvalues < x[c]
-                    const float dj = d[j], e2j = e2[j];
-#pragma unroll
-                    for (int c = 0; c < ILP; ++c) {
-                        float t = (dj - x[c]) - __fdividef(e2j, q[c]);
-                        if (fabsf(t) < pivmin) t = -pivmin;
-                        q[c] = t;
-                        cnt[c] += t < 0.f;
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < ILP; ++c)
-                    if (ej[c] >= 0) {
-                        const int idx = qd - 1 - ej[c];   // ascending index of the ej-th largest eigenvalue
-                        if (cnt[c] <= idx) atomicMax(&nlo[ej[c]], __float_as_int(x[c]));   // x is a lower bound
-                        else atomicMin(&nhi[ej[c]], __float_as_int(x[c]));                  // x is an upper bound
-                    }
                 __syncthreads();
-                for (int j = tid; j < m; j += TT) {
-                    float lo = __int_as_float(nlo[j]), hi = __int_as_float(nhi[j]);
-                    if (lo > hi) { const float mid = 0.5f * (lo + hi); lo = mid; hi = mid; }
-                    blo[j] = lo; bhi[j] = hi;
+                for (int jj = tid; jj < m; jj += TT) {
+                    float l2 = __int_as_float(nlo[jj]), h2 = __int_as_float(nhi[jj]);
+                    if (l2 > h2) { const float mid = 0.5f * (l2 + h2); l2 = mid; h2 = mid; }
+                    blo[jj] = l2; bhi[jj] = h2;
                 }
                 __syncthreads();
             }
