@@ -137,22 +137,28 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
     remaining = int(est_mask)            # until the first read-back: analytic size of the lattice
     qmin = min(qmin, max(296, remaining // 64))
     tm = L.timer
+    rows_of = [cap] * 4
     r = 0
     while True:
         buf, slot = r & 1, r & 3
         target = min(cap, max(qmin, int(remaining * frac)))
         prob = 1.0 if remaining <= target else target / remaining * 0.97
+        # rows enqueued this round: the expected draw is <= 0.97 target (the count is stale, hence an over-estimate), so
+        # target + 25 % bounds it; pixels the selection cannot place stay masked for a later round.  Late rounds thus
+        # launch a third of the CTAs of a `cap`-sized round instead of thousands that exit at once.
+        rows = min(cap, int(target * 1.25) + 256)
+        rows_of[slot] = rows
         with torch.cuda.stream(sA):
             st = L.stream_ptr()
             cnt = ws.counters4[slot]
             cnt.zero_()
             if used_bayes[buf]:
                 sA.wait_event(done_bayes[buf])                               # round r-2 is done with this buffer
-            qinds, vals, inds = ws.qinds2[buf], ws.vals2[buf], ws.inds2[buf]
+            qinds, vals, inds = ws.qinds2[buf][:rows], ws.vals2[buf][:rows], ws.inds2[buf][:rows]
             L.check(L.lib.vnlb_count_mask(L.ptr(mask), t, h, w, L.ptr(cnt), st), "vnlb_count_mask")
-            L.check(L.lib.vnlb_select_queries(L.ptr(mask), t, h, w, prob, seed, r, L.ptr(qinds), cap, L.ptr(cnt), st),
+            L.check(L.lib.vnlb_select_queries(L.ptr(mask), t, h, w, prob, seed, r, L.ptr(qinds), rows, L.ptr(cnt), st),
                     "vnlb_select_queries")
-            L.check(L.lib.vnlb_pad_queries(L.ptr(qinds), L.ptr(cnt), cap, st), "vnlb_pad_queries")
+            L.check(L.lib.vnlb_pad_queries(L.ptr(qinds), L.ptr(cnt), rows, st), "vnlb_pad_queries")
             if row_hist is not None:     # groups per image row (multi-GPU: balances the bands of the next step)
                 yq = qinds[:, 1]
                 row_hist.index_add_(0, yq.clamp(min=0), (yq >= 0).to(row_hist.dtype))
@@ -176,7 +182,7 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
         if r >= 2:                       # read back round r-2 (long finished: no stall in steady state)
             old = (r - 2) & 3
             copied[old].synchronize()
-            rem_old, nsel = int(ws.host4[old][0]), min(int(ws.host4[old][1]), cap)
+            rem_old, nsel = int(ws.host4[old][0]), min(int(ws.host4[old][1]), rows_of[old])
             if nmask0 is None:
                 nmask0 = rem_old
             nproc += nsel
@@ -187,7 +193,7 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
     # the last enqueued round (r-1) drew nothing or its groups are counted here
     last = (r - 1) & 3
     copied[last].synchronize()
-    nproc += min(int(ws.host4[last][1]), cap)
+    nproc += min(int(ws.host4[last][1]), rows_of[last])
     main.wait_stream(sA)
     main.wait_stream(sB)
     return nproc, nrounds, nmask0
