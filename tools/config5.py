@@ -26,4 +26,4 @@ for sigma in (10., 20., 50.):
                  max_mem_GB=torch.cuda.max_memory_allocated() / 1e9)
         out["sigma%d_%s" % (sigma, name)] = r
         print(sigma, name, json.dumps(r), flush=True)
-json.dump(out, open("gpurun_out/config5_r1.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/config5_r1b.json", "w"), indent=1)
