@@ -507,6 +507,26 @@ def test_bayes_gram_split_path_matches_single_kernel_and_oracle(vb, kind):
     assert np.abs(outs[1][0] - outs[0][0]).max() <= 2e-4 * np.abs(outs[0][0]).max()
 
 
+def test_bayes_large_call_is_chunked_consistently(vb):
+    """More groups than one workspace chunk (16384): every group of the big call equals the same group filtered in a small call."""
+    from vnlb_b200 import deno
+    from vnlb_b200.utils import AttrDict
+    a_gpu = gargs(vb, 0)
+    rs = np.random.RandomState(23)
+    k, nb = 100, 40
+    base = (rs.rand(nb, k, 2, 3, 7, 7) * 255).astype(np.float32)
+    small = AttrDict(noisy=cu(base.copy()), basic=torch.zeros(base.shape, device=DEV), flat=torch.zeros(nb, dtype=torch.uint8, device=DEV))
+    deno.denoise(small, a_gpu, "bayes", None)
+    B = 16384 + nb
+    reps = (B + nb - 1) // nb
+    big_n = cu(base).repeat(reps, 1, 1, 1, 1, 1)[:B].contiguous()
+    big = AttrDict(noisy=big_n, basic=torch.zeros_like(big_n), flat=torch.zeros(B, dtype=torch.uint8, device=DEV))
+    rv = deno.denoise(big, a_gpu, "bayes", None)
+    ref = small.noisy.repeat(reps, 1, 1, 1, 1, 1)[:B]
+    assert torch.equal(big.noisy, ref)          # same kernels, same inputs: bit-identical, whichever chunk a group falls in
+    assert torch.isfinite(rv).all() and float(rv.min()) > 0
+
+
 def test_e2e_fast_schedule_psnr(vb, golden_dir):
     """The throughput schedule (fused and staged) stays within the PSNR band of the parity run."""
     g = np.load(os.path.join(golden_dir, "e2e.npz"))

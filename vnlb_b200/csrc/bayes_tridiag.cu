@@ -1751,7 +1751,31 @@ static float *split_workspace(size_t bytes, cudaStream_t st) {
 }
 
 template <bool FUSED>
+static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_t st);
+
+// The split path needs a workspace of 12-37 KB per (group, channel) problem: calls with more groups than a round of the
+// throughput schedule are processed in chunks of 16384 groups (1.8 GB of workspace), stream-ordered.
+template <bool FUSED>
 static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t st) {
+    constexpr int CHUNK = 16384;
+    if (B <= CHUNK || !use_split(a.L)) return launch_bayes_chunk<FUSED>(a, B, what, st);
+    const VnlbBayesParams &P = a.P;
+    const long long rstride = (long long)P.pt * P.c * P.ps * P.ps, gstride = (long long)P.k * rstride;
+    for (int g0 = 0; g0 < B; g0 += CHUNK) {
+        BayesArgs c = a;
+        if (c.pnoisy) c.pnoisy += g0 * gstride;
+        if (c.pbasic) c.pbasic += g0 * gstride;
+        if (c.flat) c.flat += g0;
+        if (c.inds) c.inds += (long long)g0 * P.k;
+        if (c.rank_var) c.rank_var += g0;
+        const int rc = launch_bayes_chunk<FUSED>(c, B - g0 < CHUNK ? B - g0 : CHUNK, what, st);
+        if (rc != VNLB_OK) return rc;
+    }
+    return VNLB_OK;
+}
+
+template <bool FUSED>
+static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_t st) {
     const VnlbBayesParams *p = &a.P;
     cudaError_t e;
     if (use_split(a.L) && a.L.gram) {
