@@ -30,6 +30,8 @@ METRIC = "vnlb.denoise Mpx/s (steps 1+2)"
 SIGMA = 20.0
 BASE = dict(T=20, H=480, W=854)
 CPU_SAMPLE = dict(T=6, H=96, W=128)
+# multi-GPU band partition (vnlb_b200/dist.py): "auto" (default), "snake", "plain" or "weighted"; override for experiments only
+BALANCE = {"plain": False, "snake": "snake", "weighted": "weighted", "auto": "auto"}[os.environ.get("VNLB_BALANCE", "auto")]
 
 
 def load_peaks():
@@ -160,7 +162,8 @@ def run_ours(args):
 
     def call(x, stats=None):
         if world > 1:
-            return vdist.denoise_distributed(x, SIGMA, schedule="fast", params=params, stats=stats, device=device)
+            return vdist.denoise_distributed(x, SIGMA, schedule="fast", params=params, stats=stats, device=device,
+                                             balance=BALANCE)
         return vnlb_b200.denoise(x, SIGMA, gpuid=local_rank, verbose=False, schedule="fast", params=params, stats=stats)
 
     def barrier():

@@ -106,13 +106,16 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
         for step in (0, 1):
             images = alloc.allocate_images(noisy, basic, clean)
             args = get_args(params, c, step, device)
-            if not balance:
+            mode = balance
+            if mode == "auto" or mode is True:
+                mode = "snake"
+            if not mode:
                 y_range = partition_rows(h, args.ps, world, rank)
-            elif step == 1 and row_hist is not None and balance == "weighted":
+            elif step == 1 and row_hist is not None and mode == "weighted":
                 y_range = partition_rows_weighted(row_hist, args.ps, world, rank)     # balanced on step-1 group density
             else:
                 y_range = partition_rows_snake(h, args.ps, world, rank)
-            st["want_row_hist"] = bool(balance == "weighted" and step == 0 and schedule == "fast")
+            st["want_row_hist"] = bool(mode == "weighted" and step == 0 and schedule == "fast")
             step_fn(images, dflows, args, st, y_range, reduce_fn)
             if step == 0:
                 basic = images["deno"].clone()
