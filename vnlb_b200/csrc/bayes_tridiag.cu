@@ -1385,14 +1385,28 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 __syncthreads();
                 float nrm = 0.f;
                 int r = qd - 1;
-                if (fwd || bwd) {
-                    float best = fabsf(z[qd - 1]);        // twist index r = argmin |gamma_i|, gamma_i = D+_i + D-_i - (d_i - l)
-                    for (int i = qd - 2; i >= 0; --i) {
+                // twist index r = argmin |gamma_i|, gamma_i = D+_i + D-_i - (d_i - l): scanned from the top, ties to the higher index;
+                // the pair splits the scan (upper half / lower half) and combines through shared memory
+                float *sbest = sm + L.oCnt;                // round-0 Sturm counts are dead: [0, MR) upper minima, [MR, 2 MR) lower minima
+                const int mid = qd >> 1;
+                if (fwd) {
+                    float best = fabsf(z[qd - 1]);
+                    for (int i = qd - 2; i >= mid; --i) {
                         const float gam = fabsf(z[i] + zb[i] - (d[i] - l));
                         if (gam < best) { best = gam; r = i; }
                     }
+                    sbest[ev] = best; nlo[ev] = r;
+                } else if (bwd) {
+                    float best = 3.4e38f;
+                    r = 0;
+                    for (int i = mid - 1; i >= 0; --i) {
+                        const float gam = fabsf(z[i] + zb[i] - (d[i] - l));
+                        if (gam < best) { best = gam; r = i; }
+                    }
+                    sbest[MR + ev] = best; nhi[ev] = r;
                 }
                 __syncthreads();                           // every D+ / D- has been read before the solves overwrite Z
+                if (fwd || bwd) r = (sbest[MR + ev] < sbest[ev]) ? nhi[ev] : nlo[ev];
                 if (fwd) {                                 // z_r = 1; upwards with D+
                     float zi = 1.f;
                     nrm = 1.f;
@@ -1552,14 +1566,13 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
             if constexpr (!GRAM) {
                 // eigenvectors re-laid as Vt[j][r] (r contiguous, pitch MR): 4 eigenpairs per broadcast LDS.128
                 float *Vt = R + L.oVt;
-                for (int idx = tid; idx < p * (MR / 4); idx += TT)
-                    reinterpret_cast<float4 *>(Vt)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncthreads();
-                for (int r = warp; r < m; r += TT / 32)
+                // (the filter reads the first 8 * ceil(m / 8) columns of a row: columns m .. that bound are zeroed, the rest is never read)
+                const int mpad = (m + 7) & ~7;
+                for (int r = warp; r < mpad; r += TT / 32)
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
                         const int j = lane + 32 * qq;
-                        if (j < p) Vt[j * MR + r] = Z[r * ZSq + j];
+                        if (j < p) Vt[j * MR + r] = r < m ? Z[r * ZSq + j] : 0.f;
                     }
             } else {
                 // Gram trick: Z[r][nn] -> Ut[nn][r] in place (through registers), then
