@@ -1791,13 +1791,16 @@ template <bool FUSED>
 static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_t st) {
     const VnlbBayesParams *p = &a.P;
     cudaError_t e;
-    if (use_split(a.L) && a.L.gram) {
+    // the split path needs device memory for its workspace; if that cannot be had, the single-kernel path still works
+    bool split = use_split(a.L);
+    if (split) {
+        a.ws_stride = a.L.gram ? gram_ws_stride<60>(a.L.LD) : split_ws_stride<98>();
+        a.ws = split_workspace((size_t)B * p->c * a.ws_stride * sizeof(float), st);
+        if (!a.ws) { (void)cudaGetLastError(); split = false; }
+    }
+    if (split && a.L.gram) {
         constexpr int QD = 60;
         a.ws_pitch = GRAM_PITCH;
-        a.ws_stride = gram_ws_stride<QD>(a.L.LD);
-        const size_t bytes = (size_t)B * p->c * a.ws_stride * sizeof(float);
-        a.ws = split_workspace(bytes, st);
-        if (!a.ws) { set_error("%s: workspace of %zu bytes: %s", what, bytes, cudaGetErrorString(cudaGetLastError())); return VNLB_ERR_CUDA; }
         const size_t smem = (size_t)a.L.total * sizeof(float);
         constexpr int scr = tridiag_scratch_floats<QD, QD, SPLIT_NR3>();
         int ybody = a.L.p * QD > QD * QD ? a.L.p * QD : QD * QD;
@@ -1815,15 +1818,11 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
         return check_launch(what, 3);
     }
-    if (use_split(a.L)) {
+    if (split) {
         a.L = tri_layout(a.L.n, a.L.p, true);            // no covariance matrix in the eigen/filter kernel
         a.ws_pitch = 100;
         const size_t smem = (size_t)a.L.total * sizeof(float);
         constexpr int QD = 98;
-        a.ws_stride = split_ws_stride<QD>();
-        const size_t bytes = (size_t)B * p->c * a.ws_stride * sizeof(float);
-        a.ws = split_workspace(bytes, st);
-        if (!a.ws) { set_error("%s: workspace of %zu bytes: %s", what, bytes, cudaGetErrorString(cudaGetLastError())); return VNLB_ERR_CUDA; }
         constexpr int scr1 = tridiag_scratch_floats<QD, QD, SPLIT_NR2>();
         const int yrows = a.L.n > 100 ? a.L.n : 100;
         const int ybody = yrows * 100 > scr1 ? yrows * 100 : scr1;
