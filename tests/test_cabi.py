@@ -44,3 +44,15 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     rc = _lib.lib.vnlb_search_topk(ctypes.c_void_p(8), 4, 3, 32, 32, ctypes.c_void_p(8), 1, None, None,
                                    ctypes.byref(p), ctypes.c_void_p(8), ctypes.c_void_p(8), None, 0, None)
     assert rc == _lib.ERR_BAD_ARG
+
+
+def test_switches_and_counters_without_a_gpu():
+    """vnlb_set_bayes_split returns the previous setting; vnlb_kernel_launches is a monotonic counter (0 launches here)."""
+    from vnlb_b200 import _lib
+    prev = _lib.lib.vnlb_set_bayes_split(0)
+    assert prev in (0, 1)
+    assert _lib.lib.vnlb_set_bayes_split(1) == 0
+    assert _lib.lib.vnlb_set_bayes_split(prev) == 1
+    n0 = int(_lib.lib.vnlb_kernel_launches())
+    _lib.lib.vnlb_rgb2yuv(None, None, 1, 3, 4, 4, None)      # rejected before any launch
+    assert int(_lib.lib.vnlb_kernel_launches()) == n0
