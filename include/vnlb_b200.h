@@ -151,7 +151,9 @@ int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8_t *flat, c
  * step 1 (7x7x2, k = 100: a 98 x 98 eigenproblem per channel): on (default) = covariance + Householder
  * tridiagonalisation with the matrix in registers, in two phase kernels, followed by the eigen/filter
  * kernel; off = everything in one shared-memory kernel.  Same algorithm; results agree to rounding.
- * Returns the previous setting.  (Environment: VNLB_BAYES_SPLIT=0 disables at start-up.)  The split path keeps a
+ * on = 2 is the split path with an EXPERIMENTAL tensor-core (3xTF32 mma) version of one elimination phase: parity-tested,
+ * measured slower than the default (profiles/r1b_summary.md), kept for the next round's work.
+ * Returns the previous setting.  (Environment: VNLB_BAYES_SPLIT=0 / 2 at start-up.)  The split path keeps a
  * grow-only device workspace per (device, stream) inside the library (37 KB per group and channel, at most 16384
  * groups at a time); if that allocation fails the call runs the single-kernel path instead. */
 int vnlb_set_bayes_split(int on);

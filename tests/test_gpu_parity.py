@@ -441,7 +441,7 @@ def test_bayes_split_path_matches_single_kernel_and_oracle(vb, kind):
         pn = np.concatenate([half, half], 1)
     ref, _, _ = orc.bayes_denoise(pn.copy(), np.zeros_like(pn), np.zeros(B, bool), a_cpu)
     outs = {}
-    for split in (1, 0):
+    for split in (1, 0, 2):                       # 2 = split path with the experimental tensor-core (3xTF32 mma) 64 -> 32 phase
         prev = _lib.lib.vnlb_set_bayes_split(split)
         try:
             patches = AttrDict(noisy=cu(pn.copy()), basic=torch.zeros(shape, device=DEV),
@@ -450,7 +450,7 @@ def test_bayes_split_path_matches_single_kernel_and_oracle(vb, kind):
             outs[split] = (patches.noisy.cpu().numpy(), rv.cpu().numpy())
         finally:
             _lib.lib.vnlb_set_bayes_split(prev)
-    for split in (1, 0):
+    for split in (1, 0, 2):
         out, rv = outs[split]
         assert np.isfinite(out).all(), (kind, split)
         for b in range(B):
@@ -459,6 +459,7 @@ def test_bayes_split_path_matches_single_kernel_and_oracle(vb, kind):
     np.testing.assert_allclose(outs[1][1], outs[0][1], rtol=1e-6)          # rank_var: same covariance bits
     scale = np.abs(outs[0][0]).max()
     assert np.abs(outs[1][0] - outs[0][0]).max() <= 2e-4 * scale
+    assert np.abs(outs[2][0] - outs[0][0]).max() <= 2e-4 * scale
 
 
 @pytest.mark.parametrize("kind", ["texture", "flatmix", "duplicates"])
