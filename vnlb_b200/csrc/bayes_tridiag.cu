@@ -760,6 +760,7 @@ __global__ void __launch_bounds__(64, 8) tridiag_tail_frag_kernel(const BayesArg
     const uint32_t s0 = smem_u32(sm);
     const uint32_t aV = s0 + 16 * VL, aW = s0 + 20 * VL, aRed = s0 + 24 * VL;
     const uint32_t aD = aRed + 96, aE = aD + 4 * KN, aTau = aE + 4 * KN, aRefl = aTau + 4 * KN;
+    const uint32_t aFB = s0 + 4 * tridiag_scratch_floats<QDG, NR, CEND>();   // B-fragment table FB[col][t] = (b0, b1): 64 x 4 x 2 words, rebuilt every step
     // fragments of this warp's two bands
     float c[NBW][NTL][4];
     {
@@ -775,6 +776,7 @@ __global__ void __launch_bounds__(64, 8) tridiag_tail_frag_kernel(const BayesArg
             }
     }
     for (int j = tid; j < 6 * VL + 24; j += NT) sm[j] = 0.f;
+    for (int j = tid; j < 512; j += NT) sm[tridiag_scratch_floats<QDG, NR, CEND>() + j] = 0.f;
     __syncthreads();
     constexpr int c0 = NR - 1;
     if (t == 3) {       // columns 63 (x) and 62 (r) live in tile 7, lanes t = 3: registers 1/3 and 0/2
@@ -860,7 +862,7 @@ __global__ void __launch_bounds__(64, 8) tridiag_tail_frag_kernel(const BayesArg
         const float vcm2 = xcm2 * scale;
         const float wcm2 = fmaf(-hs, vcm2, ts * fmaf(-beta, rcm2, ycm2));
         const int cq = cc - 2, tq = (cq & 7) >> 1, odd = cq & 1;   // column c-2 sits in the window tile: lanes t = tq
-        float vr[NBW][2], wr[NBW][2];
+        uint32_t af[NBW][4];                           // A fragments: row i -> [-v_hi -v_hi -v_lo -w_hi | -w_hi -w_lo 0 0]
 #pragma unroll
         for (int q = 0; q < NBW; ++q)
 #pragma unroll
@@ -870,7 +872,6 @@ __global__ void __launch_bounds__(64, 8) tridiag_tail_frag_kernel(const BayesArg
                 float vi = (i == cc - 1) ? 1.f : xi[q][h] * scale;
                 float wi = fmaf(-hs, vi, ts * fmaf(-beta, ri[q][h], yi[q][h]));
                 if (!act) { vi = 0.f; wi = 0.f; }
-                vr[q][h] = vi; wr[q][h] = wi;
                 const float xnext = fmaf(-vi, wcm1, fmaf(-wi, 1.f, ri[q][h]));
                 if (t == 0) {
                     if (act) {
@@ -886,30 +887,24 @@ __global__ void __launch_bounds__(64, 8) tridiag_tail_frag_kernel(const BayesArg
                     const float qi = odd ? (h ? wn[q][3] : wn[q][1]) : (h ? wn[q][2] : wn[q][0]);
                     sts32(aRn + 4 * i, fmaf(-vi, wcm2, fmaf(-wi, vcm2, qi)));
                 }
+                // TF32 splits once per row and step; the 4 lanes of a row publish the 4 (b0, b1) pairs of COLUMN i
+                const uint32_t vh = f2tf32(vi), wh = f2tf32(wi);
+                const uint32_t vl = f2tf32(vi - __uint_as_float(vh)), wl = f2tf32(wi - __uint_as_float(wh));
+                const uint32_t b0 = t == 0 ? wh : (t == 1 ? wl : (t == 2 ? wh : vh));     // k = t     of [w_hi w_lo w_hi v_hi v_lo v_hi 0 0]
+                const uint32_t b1 = t == 0 ? vl : (t == 1 ? vh : 0u);                     // k = t + 4
+                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(aFB + 8 * (4 * i + t)), "r"(b0), "r"(b1) : "memory");
+                const uint32_t sgn = 0x80000000u;          // negation is exact in TF32
+                af[q][h] = (t == 0 ? vh : (t == 1 ? vh : (t == 2 ? vl : wh))) ^ sgn;      // k = t     of [-v_hi -v_hi -v_lo -w_hi -w_hi -w_lo 0 0]
+                af[q][2 + h] = t == 0 ? (wh ^ sgn) : (t == 1 ? (wl ^ sgn) : 0u);          // k = t + 4
             }
         if (tid == 0) { sts32(aD + 4 * k, dk); sts32(aE + 4 * k, beta); sts32(aTau + 4 * k, tau); }
         bar_sync_n(1, NT);                                                            // B2
-        // A fragments of the two bands: row i -> [-v_hi -v_hi -v_lo -w_hi | -w_hi -w_lo 0 0]
-        uint32_t af[NBW][4];
-#pragma unroll
-        for (int q = 0; q < NBW; ++q)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t vh = f2tf32(-vr[q][h]), wh = f2tf32(-wr[q][h]);
-                const uint32_t vl = f2tf32(-vr[q][h] - __uint_as_float(vh)), wl = f2tf32(-wr[q][h] - __uint_as_float(wh));
-                af[q][h] = t == 0 ? vh : (t == 1 ? vh : (t == 2 ? vl : wh));          // k = t
-                af[q][2 + h] = t == 0 ? wh : (t == 1 ? wl : 0u);                      // k = t + 4
-            }
         float yn[NBW][2];
 #pragma unroll
         for (int q = 0; q < NBW; ++q) { yn[q][0] = 0.f; yn[q][1] = 0.f; }
         const bool live0 = 16 * warp < cc, live1 = 16 * (warp + 2) < cc;
         auto bfrag = [&](int col, uint32_t &b0, uint32_t &b1) {     // B fragment of column `col` for this lane's k = t, t + 4
-            const float vc = lds32(aV + 4 * col), wc = lds32(aW + 4 * col);
-            const uint32_t vh = f2tf32(vc), wh = f2tf32(wc);
-            const uint32_t vl = f2tf32(vc - __uint_as_float(vh)), wl = f2tf32(wc - __uint_as_float(wh));
-            b0 = t == 0 ? wh : (t == 1 ? wl : (t == 2 ? wh : vh));
-            b1 = t == 0 ? vl : (t == 1 ? vh : 0u);
+            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(aFB + 8 * (4 * col + t)));
         };
 #define VNLB_FT(J)                                                                        \
         case (J) + 1: {                                                                   \
@@ -2091,7 +2086,7 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
         k1<<<B * p->c, TT, smem1, st>>>(a);
         const bool frag = g_split == 2;                     // vnlb_set_bayes_split(2): experimental tensor-core version of the 64 -> 32 phase
-        if (frag) tridiag_tail_frag_kernel<QD, LDG, 4 * LDG, split_trail_off<QD>(), split_trail2_off<QD>()><<<B * p->c, 64, smem1b, st>>>(a);
+        if (frag) tridiag_tail_frag_kernel<QD, LDG, 4 * LDG, split_trail_off<QD>(), split_trail2_off<QD>()><<<B * p->c, 64, smem1b + 512 * sizeof(float), st>>>(a);
         else k1b<<<B * p->c, 64, smem1b, st>>>(a);
         k1c<<<B * p->c, 32, smem1c, st>>>(a);
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
