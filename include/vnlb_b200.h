@@ -6,10 +6,12 @@
  *   - plain pointers and sizes; every pointer is DEVICE memory unless it is a
  *     parameter struct (host memory, read during the call) ;
  *   - the caller allocates every buffer, including the workspace reported by
- *     the matching *_workspace_bytes(); the callee never allocates;
+ *     the matching *_workspace_bytes() (16-byte aligned device memory, private
+ *     to one stream at a time); the library never calls cudaMalloc / cudaFree;
  *   - stream-ordered and asynchronous: work is enqueued on `stream`
  *     (a cudaStream_t passed as void*, NULL = default stream); no entry point
- *     synchronises the device;
+ *     synchronises the device or a stream, so every call can be captured in a
+ *     CUDA graph;
  *   - return value 0 on success, VNLB_ERR_* (< 0) otherwise;
  *     vnlb_last_error() returns a thread-local description of the last failure;
  *   - re-entrant per stream; one host thread per device.
@@ -94,6 +96,12 @@ int vnlb_yuv2rgb(const float *yuv, float *rgb, int T, int C, int H, int W, void 
  * (multi-GPU sharding; pass 0, H for the reference behaviour). */
 int vnlb_init_mask(int8_t *mask, int T, int H, int W, int ps, int pt, int proc_step,
                    int y_begin, int y_end, void *stream);
+/* The same lattice for a TILE of a larger frame (multi-GPU: one row band + halo per GPU): `mask` is [T,H,W] and holds
+ * rows [y_offset, y_offset + H) of a frame of H_total rows; the lattice phase, the always-set first / last row and
+ * the valid range follow the global row, y_begin / y_end are local rows.  The union of the tiles' masks over
+ * disjoint [y_begin, y_end) bands equals the whole-frame mask of vnlb_init_mask. */
+int vnlb_init_mask_tile(int8_t *mask, int T, int H, int W, int ps, int pt, int proc_step,
+                        int y_begin, int y_end, int y_offset, int H_total, void *stream);
 
 /* vpss.exec_sim_search_burst, call site lib/vnlb/search/search.py:86-89.
  * img [T,C,H,W]; qinds int64 [Q,3] = (t,y,x) of each query's patch corner;
@@ -132,6 +140,16 @@ int vnlb_pad_queries(int64_t *qinds, const uint32_t *counters, int cap, void *st
 int vnlb_select_queries(int8_t *mask, int T, int H, int W, double prob, uint32_t seed,
                         uint32_t round, int64_t *qinds, int cap, uint32_t *counters, void *stream);
 
+/* Greedy conflict resolution inside a round of the throughput schedule (the reference resolves it by processing
+ * sub-batches of 128 sequentially, lib/vnlb/search/search.py:38-64): after vnlb_search_topk and BEFORE
+ * vnlb_mask_update, a row of `inds` whose reference pixel (its row of `qinds`) lies in the clear-set (found patches +
+ * boost neighbours) of an EARLIER valid row of the same round is dropped -- its K indices become -1, so every later
+ * kernel skips it -- and its pixel is set in the mask again (a later round draws it if nothing ends up covering it).
+ * owner: uint32 [T,H,W] scratch, filled with 0xFFFFFFFF once per step by the caller; round: 0, 1, ... within the step
+ * (stamps carry the round, the map is never cleared in between); dropped: uint32 counter, incremented. */
+int vnlb_round_dedup(const int64_t *qinds, int64_t *inds, int B, int K, uint32_t *owner, uint32_t round,
+                     int8_t *mask, int T, int C, int H, int W, int boost, uint32_t *dropped, void *stream);
+
 /* exec_flat_areas, lib/vnlb/utils/flat_areas.py:16-34.  flat: uint8 [B]
  * (0/1), written for every row (invalid rows get 0). thresh = gamma*sigma2. */
 int vnlb_flat_areas(const float *pnoisy, const int64_t *inds, uint8_t *flat, int B, int K,
@@ -141,21 +159,35 @@ int vnlb_flat_areas(const float *pnoisy, const int64_t *inds, uint8_t *flat, int
  * pnoisy [B,K,pt,C,ps,ps]; pbasic (step 2) is read only (the reference
  * re-centres it back to its input values, :52).  Rows that are not valid in
  * `inds` ([B,K], may be NULL = all valid) are skipped.  rank_var float32 [B]
- * (may be NULL).  flat uint8 [B] (may be NULL in step 1). */
+ * (may be NULL).  flat uint8 [B] (may be NULL in step 1).
+ * Workspace: the production shapes (7x7x2 patches, k = 100 in step 1 / k = 60 in step 2) run as a chain of kernels
+ * that hand (d, e, tau, mean, packed reflectors, trailing matrices) to each other through `ws`: 37 KB (step 1) /
+ * 12 KB (step 2) per (group, channel).  vnlb_bayes_workspace_bytes(B, p) = the size for min(B, 16384) groups (0 for
+ * shapes served by the single-kernel path); a smaller workspace is legal -- the call is then processed in
+ * stream-ordered chunks of as many groups as fit -- but one that cannot hold a single group is VNLB_ERR_WORKSPACE. */
 size_t vnlb_bayes_workspace_bytes(int B, const VnlbBayesParams *p);
 int vnlb_bayes_filter(float *pnoisy, const float *pbasic, const uint8_t *flat, const int64_t *inds,
                       int B, const VnlbBayesParams *p, float *rank_var, void *ws, size_t ws_bytes,
                       void *stream);
 
-/* Implementation switch of vnlb_bayes_filter / vnlb_bayes_aggregate_fused for the production patch shape of
- * step 1 (7x7x2, k = 100: a 98 x 98 eigenproblem per channel): on (default) = covariance + Householder
- * tridiagonalisation with the matrix in registers, in two phase kernels, followed by the eigen/filter
- * kernel; off = everything in one shared-memory kernel.  Same algorithm; results agree to rounding.
- * on = 2 is the split path with an EXPERIMENTAL tensor-core (3xTF32 mma) version of one elimination phase: parity-tested,
- * measured slower than the default (profiles/r1b_summary.md), kept for the next round's work.
- * Returns the previous setting.  (Environment: VNLB_BAYES_SPLIT=0 / 2 at start-up.)  The split path keeps a
- * grow-only device workspace per (device, stream) inside the library (37 KB per group and channel, at most 16384
- * groups at a time); if that allocation fails the call runs the single-kernel path instead. */
+/* Parity hook for compute_cov_mat / denoise_eigvals / bayes_filter_coeff (lib/vnlb/deno/bayes_est.py:112-144):
+ * vnlb_bayes_filter that also exports, per (group, channel) problem b*C + ch,
+ *   mat  float32 [B*C, q, q] : the matrix that is eigen-decomposed -- the covariance Y^T Y / n (q = p = pt*ps*ps), or, when
+ *                              k + 8 <= p (step 2: k = 60), the Gram matrix Y Y^T / n (q = k) whose non-zero spectrum is the
+ *                              covariance's; vnlb_bayes_matrix_dim() returns q and tells which (0 = shape not served);
+ *   lam  float32 [B*C, 40]   : the eigenvalues above the Wiener threshold thresh*sigma2 + sigmab2, descending, zero padded;
+ *   coef float32 [B*C, 40]   : their filter coefficients;   m int32 [B*C] : their number (<= rank).
+ * Any of the four may be NULL.  VNLB_EIG_TRIDIAG only; same workspace contract as vnlb_bayes_filter. */
+int vnlb_bayes_matrix_dim(const VnlbBayesParams *p, int *is_gram);
+int vnlb_bayes_debug(float *pnoisy, const float *pbasic, const uint8_t *flat, const int64_t *inds, int B,
+                     const VnlbBayesParams *p, float *mat, float *lam, float *coef, int32_t *m, void *ws,
+                     size_t ws_bytes, void *stream);
+
+/* Implementation switch of vnlb_bayes_filter / vnlb_bayes_aggregate_fused for the production patch shapes: on (default)
+ * = covariance / Gram matrix + Householder tridiagonalisation with the matrix in registers, in phase kernels, followed
+ * by the eigen/filter kernel; off = everything in one shared-memory kernel (needs no workspace).  Same algorithm;
+ * results agree to rounding.  Returns the previous setting.  (Environment: VNLB_BAYES_SPLIT=0 at start-up.)
+ * vnlb_bayes_workspace_bytes() follows the current setting. */
 int vnlb_set_bayes_split(int on);
 
 /* Fusion of vpss.fill_patches (search.py:91-98) + exec_flat_areas
@@ -164,12 +196,14 @@ int vnlb_set_bayes_split(int on);
  * (YUV) images through `inds` [B,K], filtered, and added into deno [T,C,H,W] /
  * weights [T,H,W]; the patch stacks never reach HBM.  flat_thresh =
  * gamma*sigma2 (used in step 2 only).  Same numerics as vnlb_bayes_filter with
- * VNLB_EIG_TRIDIAG.  vnlb_bayes_fused_supported() tells whether the patch
- * shape fits the kernel (p = pt*ps*ps <= 128, rank <= 40). */
+ * VNLB_EIG_TRIDIAG, same workspace contract (vnlb_bayes_workspace_bytes).
+ * vnlb_bayes_fused_supported() tells whether the patch shape fits the kernel
+ * (p = pt*ps*ps <= 128, rank <= 40); T*C*H*W must be < 2^31 (32-bit image offsets). */
 int vnlb_bayes_fused_supported(const VnlbBayesParams *p);
 int vnlb_bayes_aggregate_fused(const float *img_noisy, const float *img_basic, const int64_t *inds,
                                int B, int T, int C, int H, int W, const VnlbBayesParams *p,
-                               float flat_thresh, float *deno, float *weights, void *stream);
+                               float flat_thresh, float *deno, float *weights, void *ws, size_t ws_bytes,
+                               void *stream);
 
 /* agg_patches -> exec_agg_simple_numba, lib/vnlb/agg/comp_agg.py:47-60,106-138:
  * deno[t+dt,ch,y+dy,x+dx] += patch, weights[t+dt,y+dy,x+dx] += 1 for every

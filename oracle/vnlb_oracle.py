@@ -456,7 +456,7 @@ def compute_psnrs(deno, clean, imax=255.):
 # synthetic data: shared by tests and bench
 # ----------------------------------------------------------------------------
 
-def synth_video(T, H, W, seed=123, C=3):
+def synth_video(T, H, W, seed=123, C=3, return_flows=False):
     """Deterministic clean video: smooth field + textured rectangles that
     translate 1-2 px/frame; range 0..255, float32 [T,C,H,W].  Also returns the
     analytic forward/backward flows [T,2,H,W] (ch0 = dx, ch1 = dy) of the
@@ -464,6 +464,8 @@ def synth_video(T, H, W, seed=123, C=3):
     rng = np.random.RandomState(seed)
     yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
     vid = np.zeros((T, C, H, W), np.float32)
+    ff = np.zeros((T, 2, H, W), np.float32) if return_flows else None
+    bf = np.zeros((T, 2, H, W), np.float32) if return_flows else None
     nrect = 6
     rects = []
     for _ in range(nrect):
@@ -483,7 +485,13 @@ def synth_video(T, H, W, seed=123, C=3):
             ye, xe = min(H, ya + rh), min(W, xa + rw)
             if ye > ys and xe > xs:
                 vid[t, :, ys:ye, xs:xe] = tex[:, ys - ya:ye - ya, xs - xa:xe - xa]
-    return np.clip(vid, 0, 255).astype(np.float32)
+                if return_flows:     # the object's own translation (the last-drawn object wins, as in the frame)
+                    ff[t, 0, ys:ye, xs:xe], ff[t, 1, ys:ye, xs:xe] = vx, vy
+                    bf[t, 0, ys:ye, xs:xe], bf[t, 1, ys:ye, xs:xe] = -vx, -vy
+    vid = np.clip(vid, 0, 255).astype(np.float32)
+    if return_flows:     # "precomputed flows" of SURVEY 8d: the generator's analytic translation field, |flow| <= 2 px/frame
+        return vid, dict(fflow=ff, bflow=bf)
+    return vid
 
 
 def add_noise(clean, sigma, seed=123):

@@ -68,3 +68,9 @@ def color_inputs(seed=2):
 
 
 E2E = dict(T=4, H=40, W=48, sigma=20., seed=123, torch_seed=123)
+E2E_CASES = dict(
+    e2e=E2E,
+    e2e_s10=dict(T=4, H=40, W=48, sigma=10., seed=123, torch_seed=123),      # noise levels of BASELINE configs[4]
+    e2e_s50=dict(T=4, H=40, W=48, sigma=50., seed=123, torch_seed=123),
+    e2e_cfg1=dict(T=3, H=64, W=64, sigma=20., seed=123, torch_seed=123),     # BASELINE configs[0]: davis_64x64-shaped, 3 frames
+)

@@ -110,7 +110,18 @@ def main():
     rflat.update_flat_patch(patches, args)
     np.savez_compressed(os.path.join(HERE, "flat.npz"), flat=patches.flat.numpy())
 
-    # ---- Bayes (B1-B7) ----
+    # ---- Bayes (B1-B7), with the intermediates of compute_cov_mat / denoise_eigvals / bayes_filter_coeff (B4-B6) ----
+    import vnlb.deno.bayes_est as rbayes
+    captured = {}
+    orig_cov = rbayes.compute_cov_mat
+
+    def capture_cov(pinput, rank):
+        covMat, eigVals, eigVecs = orig_cov(pinput, rank)
+        captured["cov"], captured["evals"] = covMat.clone(), eigVals.clone()
+        captured["live"] = eigVals                      # mutated in place into the filter coefficients (bayes_est.py:41-42)
+        return covMat, eigVals, eigVecs
+
+    rbayes.compute_cov_mat = capture_cov
     for step in (0, 1):
         pn, pb, flat = gin.bayes_inputs(step)
         args = rparams.get_args(params, 3, step, "cpu")
@@ -125,6 +136,10 @@ def main():
         np.savez_compressed(os.path.join(HERE, "bayes_step%d.npz" % (step + 1)),
                             noisy=patches.noisy.numpy(), basic=patches.basic.numpy(),
                             rank_var=rank_var.numpy())
+        np.savez_compressed(os.path.join(HERE, "bayes_parts_step%d.npz" % (step + 1)),
+                            cov=captured["cov"].numpy().astype(np.float32), evals=captured["evals"].numpy(),
+                            coeff=captured["live"].numpy())
+    rbayes.compute_cov_mat = orig_cov
 
     # ---- aggregation (G1) ----
     p, inds, (T, C, H, W) = gin.agg_inputs()
@@ -141,17 +156,18 @@ def main():
     ragg.agg_patches(patches, images, bufs, args, cs_ptr=0)
     np.savez_compressed(os.path.join(HERE, "agg.npz"), deno=images.deno.numpy(), weights=images.weights.numpy())
 
-    # ---- end to end: reference vnlb.denoise (A1) with default_params ----
-    e = gin.E2E
-    clean = orc.synth_video(e["T"], e["H"], e["W"], e["seed"])
-    noisy = orc.add_noise(clean, e["sigma"], e["seed"])
-    torch.manual_seed(e["torch_seed"])
-    deno, basic, dt = vnlb.denoise(noisy.copy(), e["sigma"], gpuid=-1, verbose=False)
-    deno, basic = deno.numpy(), basic.numpy()
-    ps = [orc.compute_psnrs(a, clean).mean() for a in (noisy, basic, deno)]
-    print("e2e reference: %.2fs  psnr noisy %.3f basic %.3f deno %.3f" % (dt, *ps))
-    np.savez_compressed(os.path.join(HERE, "e2e.npz"), deno=deno, basic=basic,
-                        psnrs=np.array(ps))
+    # ---- end to end: reference vnlb.denoise (A1) with default_params: sigma 20 (e2e.npz), the noise levels of BASELINE
+    #      configs[4] (sigma 10 / 50) and BASELINE configs[0] (3 x 64 x 64, sigma 20, the reference's CPU-runnable case) ----
+    for name, e in gin.E2E_CASES.items():
+        clean = orc.synth_video(e["T"], e["H"], e["W"], e["seed"])
+        noisy = orc.add_noise(clean, e["sigma"], e["seed"])
+        torch.manual_seed(e["torch_seed"])
+        deno, basic, dt = vnlb.denoise(noisy.copy(), e["sigma"], gpuid=-1, verbose=False)
+        deno, basic = deno.numpy(), basic.numpy()
+        ps = [orc.compute_psnrs(a, clean).mean() for a in (noisy, basic, deno)]
+        print("%s reference: %.2fs  psnr noisy %.3f basic %.3f deno %.3f" % (name, dt, *ps))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), deno=deno, basic=basic, psnrs=np.array(ps),
+                            seconds=np.float64(dt))
     print("golden fixtures written to", HERE)
 
 

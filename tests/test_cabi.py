@@ -50,9 +50,47 @@ def test_switches_and_counters_without_a_gpu():
     """vnlb_set_bayes_split returns the previous setting; vnlb_kernel_launches is a monotonic counter (0 launches here)."""
     from vnlb_b200 import _lib
     prev = _lib.lib.vnlb_set_bayes_split(0)
-    assert prev in (0, 1, 2)
+    assert prev in (0, 1)
     assert _lib.lib.vnlb_set_bayes_split(1) == 0
     assert _lib.lib.vnlb_set_bayes_split(prev) == 1
     n0 = int(_lib.lib.vnlb_kernel_launches())
     _lib.lib.vnlb_rgb2yuv(None, None, 1, 3, 4, 4, None)      # rejected before any launch
     assert int(_lib.lib.vnlb_kernel_launches()) == n0
+
+
+def test_bayes_workspace_contract_without_a_gpu():
+    """vnlb_bayes_workspace_bytes reports the split path's real size (the library never allocates: ADVICE r1) and
+    a call without the workspace is refused with VNLB_ERR_WORKSPACE before any launch."""
+    from vnlb_b200 import _lib
+    p1 = _lib.BayesParams(0, 100, 7, 2, 3, 39, 400., 400., 2.7, 0, _lib.EIG_TRIDIAG)
+    p2 = _lib.BayesParams(1, 60, 7, 2, 3, 39, 400., 0., 0.7, 1, _lib.EIG_TRIDIAG)
+    prev = _lib.lib.vnlb_set_bayes_split(1)
+    try:
+        b1 = int(_lib.lib.vnlb_bayes_workspace_bytes(1, ctypes.byref(p1)))
+        b2 = int(_lib.lib.vnlb_bayes_workspace_bytes(1, ctypes.byref(p2)))
+        assert 30_000 * 3 < b1 < 45_000 * 3 and 10_000 * 3 < b2 < 18_000 * 3          # ~41 KB / ~12-16 KB per (group, channel)
+        assert int(_lib.lib.vnlb_bayes_workspace_bytes(1000, ctypes.byref(p1))) == 1000 * b1
+        assert int(_lib.lib.vnlb_bayes_workspace_bytes(10 ** 6, ctypes.byref(p1))) == 16384 * b1   # chunked beyond a round
+        p3 = _lib.BayesParams(0, 40, 5, 1, 3, 20, 400., 400., 2.7, 0, _lib.EIG_TRIDIAG)           # other shapes: single kernel
+        assert int(_lib.lib.vnlb_bayes_workspace_bytes(64, ctypes.byref(p3))) == 0
+        n0 = int(_lib.lib.vnlb_kernel_launches())
+        rc = _lib.lib.vnlb_bayes_filter(ctypes.c_void_p(16), None, None, None, 4, ctypes.byref(p1), None, None, 0, None)
+        assert rc == _lib.ERR_WORKSPACE and b"workspace" in _lib.lib.vnlb_last_error()
+        rc = _lib.lib.vnlb_bayes_aggregate_fused(ctypes.c_void_p(16), None, ctypes.c_void_p(16), 4, 4, 3, 32, 32,
+                                                 ctypes.byref(p1), 0., ctypes.c_void_p(16), ctypes.c_void_p(16),
+                                                 ctypes.c_void_p(16), b1 - 1, None)
+        assert rc == _lib.ERR_WORKSPACE
+        assert int(_lib.lib.vnlb_kernel_launches()) == n0
+        _lib.lib.vnlb_set_bayes_split(0)
+        assert int(_lib.lib.vnlb_bayes_workspace_bytes(64, ctypes.byref(p1))) == 0
+    finally:
+        _lib.lib.vnlb_set_bayes_split(prev)
+
+
+def test_library_never_allocates_or_synchronises():
+    """The header's contract, checked on the sources: no cudaMalloc / cudaFree / *Synchronize in the product library."""
+    import glob
+    for f in glob.glob(os.path.join(ROOT, "vnlb_b200", "csrc", "*.cu*")):
+        src = re.sub(r"//.*", "", open(f).read())
+        for bad in ("cudaMalloc", "cudaFree", "cudaDeviceSynchronize", "cudaStreamSynchronize"):
+            assert bad not in src, (f, bad)

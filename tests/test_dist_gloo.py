@@ -31,16 +31,6 @@ def test_partition_rows_covers_every_reference_row_once():
         assert max(sizes) - min(sizes) <= 1 and min(sizes) > 0
 
 
-def test_snake_partition_is_a_partition():
-    from vnlb_b200.dist import partition_rows_snake
-    for h, world in [(480, 2), (3840, 8), (960, 4)]:
-        rows = []
-        for r in range(world):
-            for (a, b) in partition_rows_snake(h, 7, world, r):
-                rows += list(range(a, min(b, h - 6)))
-        assert sorted(rows) == list(range(h - 6))
-
-
 def test_weighted_partition_balances_and_covers():
     from vnlb_b200.dist import partition_rows_weighted
     rs = np.random.RandomState(0)
@@ -55,40 +45,88 @@ def test_weighted_partition_balances_and_covers():
             assert max(sums) / (sum(sums) / world) < 1.05
 
 
+def test_halo_and_exchange_plan():
+    """halo = window radius + patch extent + flow drift; give/take are mirror images of each other across ranks and
+    only neighbours exchange when the bands are wider than the halo."""
+    from vnlb_b200 import get_params
+    from vnlb_b200.dist import exchange_plan, halo_rows, make_layout
+    params = get_params(20.)
+    assert halo_rows(params, 0.0) == 13 + 6
+    assert halo_rows(params, 2.0) == 13 + 6 + 15            # 6 frames x (2 + 0.5) px
+    for h, world in [(1080, 8), (480, 2), (1080, 4)]:
+        halo = halo_rows(params, 2.0)
+        bands, tiles = make_layout(h, 7, world, halo)
+        assert tiles[0][0] == 0 and tiles[-1][1] == h
+        plans = [exchange_plan(bands, tiles, r) for r in range(world)]
+        for r in range(world):
+            give, take = plans[r]
+            assert set(give) <= {r - 1, r + 1} and set(take) <= {r - 1, r + 1}
+            for s, rows in give.items():
+                assert plans[s][1][r] == rows                # what I give s is what s takes from me
+                assert rows[0] >= bands[s][0] and rows[1] <= bands[s][1]
+    # bands narrower than the halo: the plan reaches beyond the neighbours and still mirrors
+    bands, tiles = make_layout(64, 7, 8, 19)
+    plans = [exchange_plan(bands, tiles, r) for r in range(8)]
+    assert any(abs(s - 3) > 1 for s in plans[3][0])
+    for r in range(8):
+        for s, rows in plans[r][0].items():
+            assert plans[s][1][r] == rows
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from vnlb_b200.dist import allreduce_accumulators, partition_rows
-    from vnlb_b200.utils import AttrDict
-    # every rank aggregates the groups of its own band of reference pixels (oracle kernels on CPU),
-    # then the accumulators are summed: the result must equal the single-process aggregation.
-    T, C, H, W, K = 3, 3, 24, 28, 6
+    from vnlb_b200.dist import exchange_accumulators, exchange_halo, exchange_plan, gather_bands, make_layout
+    # Every rank aggregates the groups of its own band of reference pixels into the accumulators of its row TILE
+    # (band + halo, tile-local indices; oracle kernels on CPU), the border rows are exchanged, every rank normalises:
+    # the gathered result must equal the single-process aggregation + normalisation of all groups.
+    T, C, H, W, K, G, halo = 3, 3, 40, 28, 6, 60, 9
     rs = np.random.RandomState(0)
-    ty = rs.randint(0, H - 6, (40, K)); tx = rs.randint(0, W - 6, (40, K)); tt = rs.randint(0, T - 1, (40, K))
-    inds = (tt * C * H * W + ty * W + tx).astype(np.int64)
-    patches = (rs.rand(40, K, 2, C, 7, 7) * 255).astype(np.float32)
-    ref_y = ty[:, 0]                                           # band membership by the reference pixel's row
-    y0, y1 = partition_rows(H, 7, world, rank)
+    ref_y = rs.randint(0, H - 6, (G,))
+    ty = np.clip(ref_y[:, None] + rs.randint(-3, 4, (G, K)), 0, H - 7)      # neighbours within the halo (3 + 6 rows)
+    ty[:, 0] = ref_y
+    tx = rs.randint(0, W - 6, (G, K)); tt = rs.randint(0, T - 1, (G, K))
+    patches = (rs.rand(G, K, 2, C, 7, 7) * 255).astype(np.float32)
+    noisy = (rs.rand(T, C, H, W) * 255).astype(np.float32)
+    bands, tiles = make_layout(H, 7, world, halo)
+    (y0, y1), (ya, yb) = bands[rank], tiles[rank]
+    give, take = exchange_plan(bands, tiles, rank)
     mine = (ref_y >= y0) & (ref_y < y1)
-    deno = np.zeros((T, C, H, W), np.float32); weights = np.zeros((T, H, W), np.float32)
-    orc.agg_patches(deno, weights, patches[mine], inds[mine])
-    images = AttrDict(deno=torch.from_numpy(deno), weights=torch.from_numpy(weights))
-    allreduce_accumulators(images)
-    if rank == 0:
-        fd = np.zeros((T, C, H, W), np.float32); fw = np.zeros((T, H, W), np.float32)
-        orc.agg_patches(fd, fw, patches, inds)
-        out["w_equal"] = bool(np.array_equal(images.weights.numpy(), fw))
-        out["d_close"] = bool(np.allclose(images.deno.numpy(), fd, rtol=1e-5, atol=1e-3))
-        out["covered"] = int(mine.sum())
+    hb = yb - ya
+    inds_local = (tt * C * hb * W + (ty - ya) * W + tx).astype(np.int64)
+    deno = np.zeros((T, C, hb, W), np.float32); weights = np.zeros((T, hb, W), np.float32)
+    orc.agg_patches(deno, weights, patches[mine], inds_local[mine])
+    deno, weights = torch.from_numpy(deno), torch.from_numpy(weights)
+    nbytes = exchange_accumulators(deno, weights, ya, give, take)
+    dn = deno.numpy().copy()
+    orc.normalize(dn, weights.numpy(), noisy[:, :, ya:yb])
+    dn = torch.from_numpy(dn)
+    exchange_halo(dn, ya, give, take)
+    full = gather_bands(dn, ya, bands, rank, H)
+    # single-process reference
+    fd = np.zeros((T, C, H, W), np.float32); fw = np.zeros((T, H, W), np.float32)
+    orc.agg_patches(fd, fw, patches, (tt * C * H * W + ty * W + tx).astype(np.int64))
+    orc.normalize(fd, fw, noisy)
+    ok_w = np.array_equal(weights.numpy()[:, y0 - ya:y1 - ya], fw[:, y0:y1])
+    out["w_equal_%d" % rank] = bool(ok_w)
+    out["full_close_%d" % rank] = bool(np.allclose(full.numpy(), fd, rtol=1e-5, atol=1e-3))
+    out["tile_close_%d" % rank] = bool(np.allclose(dn.numpy(), fd[:, :, ya:yb], rtol=1e-5, atol=1e-3))   # halo rows too
+    out["covered_%d" % rank] = int(mine.sum())
+    out["bytes_%d" % rank] = int(nbytes)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(120)
-def test_band_aggregation_plus_allreduce_equals_single_process():
-    world, port = 2, _free_port()
+@pytest.mark.parametrize("world", [2, 3])
+def test_band_tiles_plus_border_exchange_equal_single_process(world):
+    port = _free_port()
     with mp.Manager() as mgr:
         out = mgr.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
-        assert out["w_equal"] and out["d_close"] and 0 < out["covered"] < 40
+        for r in range(world):
+            assert out["w_equal_%d" % r] and out["full_close_%d" % r] and out["tile_close_%d" % r], (r, dict(out))
+            assert 0 < out["covered_%d" % r] < 60
+        # only border strips travel: far less than a frame per rank (T x (C+1) x H x W x 4 = 53760 B)
+        assert 0 < out["bytes_0"] < 3 * 4 * 40 * 28 * 4 // 2

@@ -34,10 +34,10 @@ class BayesParams(ctypes.Structure):
 
 EXPORTS = [
     "vnlb_kernel_launches",
-    "vnlb_last_error", "vnlb_version", "vnlb_rgb2yuv", "vnlb_yuv2rgb", "vnlb_init_mask",
+    "vnlb_last_error", "vnlb_version", "vnlb_rgb2yuv", "vnlb_yuv2rgb", "vnlb_init_mask", "vnlb_init_mask_tile",
     "vnlb_search_workspace_bytes", "vnlb_search_topk", "vnlb_fill_patches", "vnlb_mask_update",
-    "vnlb_count_mask", "vnlb_select_queries", "vnlb_pad_queries",
-    "vnlb_flat_areas", "vnlb_bayes_workspace_bytes", "vnlb_bayes_filter", "vnlb_bayes_fused_supported", "vnlb_set_bayes_split", "vnlb_bayes_aggregate_fused", "vnlb_aggregate",
+    "vnlb_count_mask", "vnlb_select_queries", "vnlb_pad_queries", "vnlb_round_dedup",
+    "vnlb_flat_areas", "vnlb_bayes_workspace_bytes", "vnlb_bayes_filter", "vnlb_bayes_debug", "vnlb_bayes_matrix_dim", "vnlb_bayes_fused_supported", "vnlb_set_bayes_split", "vnlb_bayes_aggregate_fused", "vnlb_aggregate",
     "vnlb_normalize",
 ]
 
@@ -58,6 +58,7 @@ _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_
 lib.vnlb_rgb2yuv.argtypes = [_vp, _vp, _i, _i, _i, _i, _vp]
 lib.vnlb_yuv2rgb.argtypes = [_vp, _vp, _i, _i, _i, _i, _vp]
 lib.vnlb_init_mask.argtypes = [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
+lib.vnlb_init_mask_tile.argtypes = [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
 lib.vnlb_search_workspace_bytes.argtypes = [_i, ctypes.POINTER(SearchParams)]
 lib.vnlb_search_topk.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, ctypes.POINTER(SearchParams),
                                  _vp, _vp, _vp, _sz, _vp]
@@ -66,12 +67,15 @@ lib.vnlb_mask_update.argtypes = [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]
 lib.vnlb_count_mask.argtypes = [_vp, _i, _i, _i, _vp, _vp]
 lib.vnlb_select_queries.argtypes = [_vp, _i, _i, _i, ctypes.c_double, ctypes.c_uint32, ctypes.c_uint32, _vp, _i, _vp, _vp]
 lib.vnlb_pad_queries.argtypes = [_vp, _vp, _i, _vp]
+lib.vnlb_round_dedup.argtypes = [_vp, _vp, _i, _i, _vp, ctypes.c_uint32, _vp, _i, _i, _i, _i, _i, _vp, _vp]
 lib.vnlb_flat_areas.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]
 lib.vnlb_bayes_workspace_bytes.argtypes = [_i, ctypes.POINTER(BayesParams)]
 lib.vnlb_bayes_filter.argtypes = [_vp, _vp, _vp, _vp, _i, ctypes.POINTER(BayesParams), _vp, _vp, _sz, _vp]
+lib.vnlb_bayes_debug.argtypes = [_vp, _vp, _vp, _vp, _i, ctypes.POINTER(BayesParams), _vp, _vp, _vp, _vp, _vp, _sz, _vp]
+lib.vnlb_bayes_matrix_dim.argtypes = [ctypes.POINTER(BayesParams), ctypes.POINTER(ctypes.c_int)]
 lib.vnlb_bayes_fused_supported.argtypes = [ctypes.POINTER(BayesParams)]
 lib.vnlb_set_bayes_split.argtypes = [_i]
-lib.vnlb_bayes_aggregate_fused.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(BayesParams), _f, _vp, _vp, _vp]
+lib.vnlb_bayes_aggregate_fused.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(BayesParams), _f, _vp, _vp, _vp, _sz, _vp]
 lib.vnlb_aggregate.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
 lib.vnlb_normalize.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp]
 

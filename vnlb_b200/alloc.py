@@ -43,6 +43,23 @@ def allocate_images(noisy, basic, clean):
     return imgs
 
 
+def allocate_images_lean(noisy_yuv, basic_yuv, clean_yuv=None):
+    """Image set of the throughput schedule: the inputs are ALREADY in YUV (converted once per call by the caller, not
+    once per step), `basic` stays None in step 1 (the reference gathers an all-zero image there, alloc.py:45-50), and
+    only the accumulators are zero-filled -- no `vals` image (never read: comp_agg.py:140-141)."""
+    imgs = AttrDict()
+    imgs.noisy, imgs.basic, imgs.clean = noisy_yuv, basic_yuv, clean_yuv
+    imgs.shape, imgs.device = noisy_yuv.shape, noisy_yuv.device
+    t, c, h, w = noisy_yuv.shape
+    imgs.deno = torch.zeros((t, c, h, w), dtype=torch.float32, device=noisy_yuv.device)
+    imgs.weights = torch.zeros((t, h, w), dtype=torch.float32, device=noisy_yuv.device)
+    imgs.vals = None
+    imgs.is_yuv = True
+    imgs.patch_images = ["noisy", "basic", "clean"]
+    imgs.ikeys = ["noisy", "basic", "clean", "deno"]
+    return imgs
+
+
 def allocate_flows(shape, device):
     """Zero flows.  The search treats fflow = bflow = None as zero flow, so no
     [T,2,H,W] tensors are materialised (reference: alloc.py:66-72)."""

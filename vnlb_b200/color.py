@@ -22,6 +22,15 @@ def yuv2rgb(burst, cs_ptr=None):
     return burst
 
 
+def yuv2rgb_new(burst, cs_ptr=None):
+    """Out-of-place yuv2rgb (the input keeps its YUV values)."""
+    t, c, h, w = burst.shape
+    out = torch.empty_like(burst)
+    L.check(L.lib.vnlb_yuv2rgb(L.ptr(burst, torch.float32), L.ptr(out), t, c, h, w, L.stream_ptr(cs_ptr)),
+            "vnlb_yuv2rgb")
+    return out
+
+
 def rgb2yuv_images(images):
     for key in images.ikeys:
         if images[key] is None:

@@ -30,7 +30,6 @@
 //     patch stacks, vpss.fill_patches, exec_flat_areas and agg_patches never touch HBM.
 #include <stdlib.h>
 
-#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -134,6 +133,12 @@ struct BayesArgs {
     // common
     const long long *inds;
     float *rank_var;
+    // parity hook (vnlb_bayes_debug, stack mode): the matrix that is eigen-decomposed, the eigenvalues above the Wiener
+    // threshold (descending), their filter coefficients and their number, per (group, channel) problem; all may be null
+    float *dbg_mat;                // [B*C, q, q]   covariance (q = p) or Gram matrix (q = n), natural index order
+    float *dbg_lam;                // [B*C, MR]
+    float *dbg_coef;               // [B*C, MR]
+    int *dbg_m;                    // [B*C]
     float *ws;                     // split path: per-problem workspace (see cov_tridiag_kernel)
     int ws_stride;                 // floats per problem
     int ws_pitch;                  // floats per (d | e | tau) vector in the workspace
@@ -691,6 +696,13 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
         }
         dg = Ar[min(tid, QD - 1)] * live;            // diagonal entry (already divided by n)
     }
+    if (a.dbg_mat) {                                 // parity hook: the covariance in natural (un-reversed) index order
+        float *o = a.dbg_mat + (size_t)blockIdx.x * QD * QD;
+        for (int idx = threadIdx.x; idx < QD * QD; idx += TT) {
+            const int i = idx / QD, j = idx - i * QD;
+            o[idx] = Y[(QD - 1 - i) * LDQ + (QD - 1 - j)];
+        }
+    }
     __syncthreads();                                 // A is dead
     if (a.rank_var) {                                // rank_var = mean over channels of trace(C) (bayes_est.py:39-40)
         float tr = warp_sum(dg);
@@ -724,249 +736,6 @@ __global__ void __launch_bounds__(NT, OCC) tridiag_tail_kernel(const BayesArgs a
         b[2 * I + 1] = make_float2(f.z, f.w);
     }
     tridiag_regs<QDG, NR, CEND, NT, NCH, OPITCH, OREFL>(b, sm, wsp, wsp + TOUT, tid);
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL (vnlb_set_bayes_split(2) / VNLB_BAYES_SPLIT=2; off by default): phase 64 -> 32 with the trailing matrix held in mma ACCUMULATOR
-// FRAGMENTS, the rank-2 update on the tensor cores.  Warp w owns the 16-row bands w and w+2; a band is 8 column
-// tiles of m16n8k8 fragments (lane (g, t): rows g, g+8, columns 2t, 2t+1 of a tile).  Per tile and step
-//     B <- B - v w^T - w v^T  =  C + [-v_hi -v_hi -v_lo -w_hi -w_hi -w_lo 0 0] . [w_hi w_lo w_hi v_hi v_lo v_hi 0 0]^T
-// is ONE 3xTF32 mma (the lo*lo terms, 2^-22 relative, are dropped; tools/proto_mma_sweep.py: same accuracy as FP32);
-// the B fragment comes from two scalar LDS per tile (shared by the warp's bands), the A fragment from the row scalars.
-// The mat-vec of the next step reads the updated fragments (4 FFMA + one LDS.64 per tile and band, two shuffles per
-// row pair at the end).  Shared-memory wavefronts per tile and 32 rows: 4 instead of 12 in tridiag_regs.
-// Everything else (raw-column trick, two named barriers per step, smem layout, outputs) is tridiag_regs'.
-__device__ __forceinline__ uint32_t f2tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float2 lds64(uint32_t a) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-    return v;
-}
-
-template <int QDG, int OPITCH, int OREFL, int TIN, int TOUT>
-__global__ void __launch_bounds__(64, 8) tridiag_tail_frag_kernel(const BayesArgs a) {
-    constexpr int NR = 64, CEND = 32, NT = 64, NTL = NR / 8, NBW = 2, LDQ = 64, VL = LDQ + 4;
-    constexpr int K0 = QDG - NR, K1 = QDG - 1 - CEND, KN = (K1 - K0 + 1 + 2 + 3) & ~3;
-    constexpr int R0 = refl_off(QDG, K0), R1 = refl_off(QDG, K1 + 1);
-    extern __shared__ __align__(16) float sm[];
-    float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
-    if (wsp[3 * OPITCH - 1] == 0.f) return;           // group skipped by the first kernel
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-    const uint32_t s0 = smem_u32(sm);
-    const uint32_t aV = s0 + 16 * VL, aW = s0 + 20 * VL, aRed = s0 + 24 * VL;
-    const uint32_t aD = aRed + 96, aE = aD + 4 * KN, aTau = aE + 4 * KN, aRefl = aTau + 4 * KN;
-    const uint32_t aFB = s0 + 4 * tridiag_scratch_floats<QDG, NR, CEND>();   // B-fragment table FB[col][t] = (b0, b1): 64 x 4 x 2 words, rebuilt every step
-    // fragments of this warp's two bands
-    float c[NBW][NTL][4];
-    {
-        const float *M = wsp + TIN;
-#pragma unroll
-        for (int q = 0; q < NBW; ++q)
-#pragma unroll
-            for (int j = 0; j < NTL; ++j) {
-                const int row = 16 * (warp + 2 * q) + g, col = 8 * j + 2 * t;
-                const float2 lo = *reinterpret_cast<const float2 *>(M + row * NR + col);
-                const float2 hi = *reinterpret_cast<const float2 *>(M + (row + 8) * NR + col);
-                c[q][j][0] = lo.x; c[q][j][1] = lo.y; c[q][j][2] = hi.x; c[q][j][3] = hi.y;
-            }
-    }
-    for (int j = tid; j < 6 * VL + 24; j += NT) sm[j] = 0.f;
-    for (int j = tid; j < 512; j += NT) sm[tridiag_scratch_floats<QDG, NR, CEND>() + j] = 0.f;
-    __syncthreads();
-    constexpr int c0 = NR - 1;
-    if (t == 3) {       // columns 63 (x) and 62 (r) live in tile 7, lanes t = 3: registers 1/3 and 0/2
-#pragma unroll
-        for (int q = 0; q < NBW; ++q)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = 16 * (warp + 2 * q) + g + 8 * h;
-                const float x0 = c[q][NTL - 1][h ? 3 : 1], r0 = c[q][NTL - 1][h ? 2 : 0];
-                if (i < c0) { sts32(s0 + 4 * i, x0); sts32(s0 + 4 * (VL + i), r0); }
-                if (i == c0) sts32(aRed + 24, x0);
-            }
-    }
-    int jw = (c0 - 2) >> 3;                          // window: copy of tile column jw of both bands
-    float wn[NBW][4];
-#pragma unroll
-    for (int q = 0; q < NBW; ++q)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) wn[q][r] = c[q][NTL - 1][r];
-    __syncthreads();
-    float yi[NBW][2];
-#pragma unroll
-    for (int q = 0; q < NBW; ++q) { yi[q][0] = 0.f; yi[q][1] = 0.f; }
-#pragma unroll
-    for (int j = 0; j < NTL; ++j) {                  // y = B x for the first column
-        const float2 x2 = lds64(s0 + 4 * (8 * j + 2 * t));
-#pragma unroll
-        for (int q = 0; q < NBW; ++q) {
-            yi[q][0] = fmaf(c[q][j][1], x2.y, fmaf(c[q][j][0], x2.x, yi[q][0]));
-            yi[q][1] = fmaf(c[q][j][3], x2.y, fmaf(c[q][j][2], x2.x, yi[q][1]));
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < NBW; ++q)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            yi[q][h] += __shfl_xor_sync(0xffffffffu, yi[q][h], 1);
-            yi[q][h] += __shfl_xor_sync(0xffffffffu, yi[q][h], 2);
-        }
-    for (int cc = NR - 1; cc >= CEND; --cc) {
-        const int k = NR - 1 - cc;
-        const uint32_t pp = k & 1;
-        const uint32_t aX = s0 + pp * (8 * VL), aR = aX + 4 * VL, aXn = s0 + (pp ^ 1) * (8 * VL), aRn = aXn + 4 * VL;
-        const uint32_t aRd = aRed + pp * 48, aRdn = aRed + (pp ^ 1) * 48;
-        float xi[NBW][2], ri[NBW][2];
-        float part = 0.f;
-#pragma unroll
-        for (int q = 0; q < NBW; ++q)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = 16 * (warp + 2 * q) + g + 8 * h;
-                const bool act = i < cc;
-                xi[q][h] = act ? lds32(aX + 4 * i) : 0.f;
-                ri[q][h] = act ? lds32(aR + 4 * i) : 0.f;
-                if (t == 0) {
-                    part = fmaf(xi[q][h], yi[q][h], part);
-                    if (i == cc) sts32(aRd + 16, yi[q][h]);
-                    if (i == cc - 1) sts32(aRd + 20, yi[q][h]);
-                    if (i == cc - 2) sts32(aRd + 36, yi[q][h]);
-                }
-            }
-        part = warp_sum(part);
-        if (lane == 0) sts32(aRd + 4 * warp, part);
-        bar_sync_n(1, NT);                                                            // B1
-        const float4 r0 = lds128(aRd), r1 = lds128(aRd + 16);
-        const float ycm2 = lds32(aRd + 36);
-        const float alpha = lds32(aX + 4 * (cc - 1)), bcc = lds32(aR + 4 * (cc - 1));
-        const float xcm2 = lds32(aX + 4 * (cc - 2)), rcm2 = lds32(aR + 4 * (cc - 2));
-        const float xBx = r0.x + r0.y;
-        const float a2 = alpha * alpha;
-        const float nrm2 = fmaxf(r1.x, a2), ycm1 = r1.y, dk = r1.z;
-        const bool skip = (nrm2 == a2);
-        const float rsq = rsqrt_approx(nrm2);
-        float sq = nrm2 * rsq;
-        sq = fmaf(0.5f * rsq, fmaf(-sq, sq, nrm2), sq);
-        const float beta = skip ? alpha : -copysignf(sq, alpha);
-        const float tau = skip ? 0.f : (beta - alpha) * rcp_newton(beta);
-        const float scale = skip ? 0.f : rcp_newton(alpha - beta);
-        const float ts = tau * scale;
-        const float uBu = fmaf(beta * beta, bcc, fmaf(-2.f * beta, ycm1, xBx));
-        const float hs = 0.5f * ts * ts * uBu;
-        const float wcm1 = fmaf(-hs, 1.f, ts * fmaf(-beta, bcc, ycm1));
-        const float vcm2 = xcm2 * scale;
-        const float wcm2 = fmaf(-hs, vcm2, ts * fmaf(-beta, rcm2, ycm2));
-        const int cq = cc - 2, tq = (cq & 7) >> 1, odd = cq & 1;   // column c-2 sits in the window tile: lanes t = tq
-        uint32_t af[NBW][4];                           // A fragments: row i -> [-v_hi -v_hi -v_lo -w_hi | -w_hi -w_lo 0 0]
-#pragma unroll
-        for (int q = 0; q < NBW; ++q)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = 16 * (warp + 2 * q) + g + 8 * h;
-                const bool act = i < cc;
-                float vi = (i == cc - 1) ? 1.f : xi[q][h] * scale;
-                float wi = fmaf(-hs, vi, ts * fmaf(-beta, ri[q][h], yi[q][h]));
-                if (!act) { vi = 0.f; wi = 0.f; }
-                const float xnext = fmaf(-vi, wcm1, fmaf(-wi, 1.f, ri[q][h]));
-                if (t == 0) {
-                    if (act) {
-                        sts32(aV + 4 * i, vi);
-                        sts32(aW + 4 * i, wi);
-                        sts32(aRefl + 4 * (refl_off(QDG, K0 + k) - R0 + (cc - 1 - i)), vi);
-                        sts32(aXn + 4 * i, (i < cc - 1) ? xnext : 0.f);
-                        if (i == cc - 1) sts32(aRdn + 24, xnext);
-                    }
-                    if (i == cc) sts32(aXn + 4 * i, 0.f);
-                }
-                if (t == tq && act) {
-                    const float qi = odd ? (h ? wn[q][3] : wn[q][1]) : (h ? wn[q][2] : wn[q][0]);
-                    sts32(aRn + 4 * i, fmaf(-vi, wcm2, fmaf(-wi, vcm2, qi)));
-                }
-                // TF32 splits once per row and step; the 4 lanes of a row publish the 4 (b0, b1) pairs of COLUMN i
-                const uint32_t vh = f2tf32(vi), wh = f2tf32(wi);
-                const uint32_t vl = f2tf32(vi - __uint_as_float(vh)), wl = f2tf32(wi - __uint_as_float(wh));
-                const uint32_t b0 = t == 0 ? wh : (t == 1 ? wl : (t == 2 ? wh : vh));     // k = t     of [w_hi w_lo w_hi v_hi v_lo v_hi 0 0]
-                const uint32_t b1 = t == 0 ? vl : (t == 1 ? vh : 0u);                     // k = t + 4
-                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(aFB + 8 * (4 * i + t)), "r"(b0), "r"(b1) : "memory");
-                const uint32_t sgn = 0x80000000u;          // negation is exact in TF32
-                af[q][h] = (t == 0 ? vh : (t == 1 ? vh : (t == 2 ? vl : wh))) ^ sgn;      // k = t     of [-v_hi -v_hi -v_lo -w_hi -w_hi -w_lo 0 0]
-                af[q][2 + h] = t == 0 ? (wh ^ sgn) : (t == 1 ? (wl ^ sgn) : 0u);          // k = t + 4
-            }
-        if (tid == 0) { sts32(aD + 4 * k, dk); sts32(aE + 4 * k, beta); sts32(aTau + 4 * k, tau); }
-        bar_sync_n(1, NT);                                                            // B2
-        float yn[NBW][2];
-#pragma unroll
-        for (int q = 0; q < NBW; ++q) { yn[q][0] = 0.f; yn[q][1] = 0.f; }
-        const bool live0 = 16 * warp < cc, live1 = 16 * (warp + 2) < cc;
-        auto bfrag = [&](int col, uint32_t &b0, uint32_t &b1) {     // B fragment of column `col` for this lane's k = t, t + 4
-            asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(aFB + 8 * (4 * col + t)));
-        };
-#define VNLB_FT(J)                                                                        \
-        case (J) + 1: {                                                                   \
-            uint32_t b0, b1;                                                              \
-            bfrag(8 * (J) + g, b0, b1);                                                   \
-            const float2 x2 = lds64(aXn + 4 * (8 * (J) + 2 * t));                         \
-            if (live0) {                                                                  \
-                mma_tf32(c[0][J], af[0][0], af[0][1], af[0][2], af[0][3], b0, b1);        \
-                yn[0][0] = fmaf(c[0][J][1], x2.y, fmaf(c[0][J][0], x2.x, yn[0][0]));      \
-                yn[0][1] = fmaf(c[0][J][3], x2.y, fmaf(c[0][J][2], x2.x, yn[0][1]));      \
-            }                                                                             \
-            if (live1) {                                                                  \
-                mma_tf32(c[1][J], af[1][0], af[1][1], af[1][2], af[1][3], b0, b1);        \
-                yn[1][0] = fmaf(c[1][J][1], x2.y, fmaf(c[1][J][0], x2.x, yn[1][0]));      \
-                yn[1][1] = fmaf(c[1][J][3], x2.y, fmaf(c[1][J][2], x2.x, yn[1][1]));      \
-            }                                                                             \
-        }
-        switch ((cc + 7) >> 3) { VNLB_FT(7) VNLB_FT(6) VNLB_FT(5) VNLB_FT(4) VNLB_FT(3) VNLB_FT(2) VNLB_FT(1) VNLB_FT(0) default: break; }
-#undef VNLB_FT
-        {   // the window copy gets the same update
-            uint32_t b0, b1;
-            bfrag(8 * jw + g, b0, b1);
-            mma_tf32(wn[0], af[0][0], af[0][1], af[0][2], af[0][3], b0, b1);
-            mma_tf32(wn[1], af[1][0], af[1][1], af[1][2], af[1][3], b0, b1);
-        }
-#pragma unroll
-        for (int q = 0; q < NBW; ++q)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                yn[q][h] += __shfl_xor_sync(0xffffffffu, yn[q][h], 1);
-                yn[q][h] += __shfl_xor_sync(0xffffffffu, yn[q][h], 2);
-                yi[q][h] = yn[q][h];
-            }
-        if (((cc - 3) >> 3) != jw) {                 // next step needs column c-3: re-read the window from the fragments
-            jw = (cc - 3) >> 3;
-            switch (jw) {
-#define VNLB_FW(J) case (J): { _Pragma("unroll") for (int r = 0; r < 4; ++r) { wn[0][r] = c[0][J][r]; wn[1][r] = c[1][J][r]; } } break;
-                VNLB_FW(0) VNLB_FW(1) VNLB_FW(2) VNLB_FW(3) VNLB_FW(4) VNLB_FW(5) VNLB_FW(6) VNLB_FW(7)
-#undef VNLB_FW
-                default: break;
-            }
-        }
-    }
-    // trailing CEND x CEND matrix for the next phase: bands 0 and 1 (q = 0 of both warps), tiles 0 .. CEND/8 - 1
-    {
-        float *trail = wsp + TOUT;
-        const int row = 16 * warp + g;
-#pragma unroll
-        for (int j = 0; j < CEND / 8; ++j) {
-            *reinterpret_cast<float2 *>(trail + row * CEND + 8 * j + 2 * t) = make_float2(c[0][j][0], c[0][j][1]);
-            *reinterpret_cast<float2 *>(trail + (row + 8) * CEND + 8 * j + 2 * t) = make_float2(c[0][j][2], c[0][j][3]);
-        }
-    }
-    __syncthreads();
-    constexpr int NK = K1 - K0 + 1;
-    const float *sd = sm + 6 * VL + 24;
-    for (int idx = threadIdx.x; idx < NK; idx += NT) {
-        wsp[K0 + idx] = sd[idx];
-        wsp[OPITCH + K0 + idx] = sd[KN + idx];
-        wsp[2 * OPITCH + K0 + idx] = sd[2 * KN + idx];
-    }
-    for (int idx = threadIdx.x; idx < R1 - R0; idx += NT) wsp[OREFL + R0 + idx] = sd[3 * KN + idx];
 }
 
 
@@ -1131,6 +900,13 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
             b[2 * jj + 1] = make_float2(f.z * live, f.w * live);
         }
         dg = Ar[min(tid, QD - 1)] * live;
+    }
+    if (a.dbg_mat) {                                 // parity hook: the Gram matrix in natural (un-reversed) patch order
+        float *o = a.dbg_mat + (size_t)blockIdx.x * QD * QD;
+        for (int idx = threadIdx.x; idx < QD * QD; idx += NT) {
+            const int i = idx / QD, j = idx - i * QD;
+            o[idx] = Yt[(QD - 1 - i) * LDQ + (QD - 1 - j)];
+        }
     }
     __syncthreads();                                 // A is dead
     if (a.rank_var) {                                // rank_var = mean over channels of trace(C) = trace(G) (bayes_est.py:39-40)
@@ -1383,6 +1159,10 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
         {   // rank_var = mean over channels of trace(C) (bayes_est.py:39-40)
             const float tr = block_sum(tid < qd ? A[tid * LDq + tid] : 0.f, red, phase);
             if (a.rank_var && tid == 0) atomicAdd(&a.rank_var[g], tr / (float)C);
+        }
+        if (a.dbg_mat) {                             // parity hook
+            float *o = a.dbg_mat + (size_t)(g * C + ch) * qd * qd;
+            for (int idx = threadIdx.x; idx < qd * qd; idx += TT) { const int i = idx / qd; o[idx] = A[i * LDq + (idx - i * qd)]; }
         }
 
         // -------------------------------------------------------------- 1. tridiagonalisation
@@ -1850,6 +1630,13 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
         }
         __syncthreads();
 
+        if (a.dbg_lam && threadIdx.x < MR) {             // parity hook: eigenvalues above the threshold and their coefficients
+            const size_t o = (size_t)(g * C + ch) * MR + threadIdx.x;
+            const bool live = (int)threadIdx.x < m;
+            a.dbg_lam[o] = live ? lam[threadIdx.x] : 0.f;
+            if (a.dbg_coef) a.dbg_coef[o] = live ? coef[threadIdx.x] : 0.f;
+            if (a.dbg_m && threadIdx.x == 0) a.dbg_m[g * C + ch] = m;
+        }
         // -------------------------------------------------------------- 5. Wiener filter of the noisy patches
         float *X = R + L.oX;                             // X[xrows][XS], XS odd => conflict-free rows
         const float *Vt = R + L.oVt;
@@ -1963,68 +1750,63 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
 // direct covariance); VNLB_BAYES_SPLIT=0 forces the single-kernel shared-memory path.
 static int g_split = -1;   // -1: not read yet; VNLB_BAYES_SPLIT=0 in the environment or vnlb_set_bayes_split(0) disables
 static bool use_split(const TriLayout &L) {
-    if (g_split < 0) { const char *s = getenv("VNLB_BAYES_SPLIT"); g_split = (s && s[0] == '0') ? 0 : ((s && s[0] == '2') ? 2 : 1); }
+    if (g_split < 0) { const char *s = getenv("VNLB_BAYES_SPLIT"); g_split = (s && s[0] == '0') ? 0 : 1; }
     if (g_split == 0) return false;
     if (!L.gram) return L.q == 98 && (size_t)(L.n * 100 + L.n + 16) * sizeof(float) <= 72 * 1024;   // step 1: 7x7x2, direct covariance
     return L.q == 60 && L.n == 60 && L.p == 98;                                                       // step 2: 7x7x2, k = 60, Gram trick
 }
 int set_bayes_split(int on) {
     const int prev = g_split < 0 ? 1 : g_split;
-    g_split = on == 2 ? 2 : (on ? 1 : 0);              // 2: split path with the experimental tensor-core 64 -> 32 phase
+    g_split = on ? 1 : 0;
     return prev;
 }
 
-// Workspace of the split path: one grow-only buffer per (device, stream), so that the two kernels of a call and
-// the calls of one stream re-use it in stream order without allocator traffic (1 GB for 16384 groups x 3 channels).
-static float *split_workspace(size_t bytes, cudaStream_t st) {
-    struct Slot { int dev; cudaStream_t st; float *p; size_t bytes; };
-    static Slot slots[16];
-    static int nslots = 0;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lock(mu);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    Slot *s = nullptr;
-    for (int i = 0; i < nslots; ++i)
-        if (slots[i].dev == dev && slots[i].st == st) s = &slots[i];
-    if (!s) {
-        if (nslots == 16) {   // recycle the oldest slot
-            cudaDeviceSynchronize();
-            cudaFree(slots[0].p);
-            for (int i = 1; i < 16; ++i) slots[i - 1] = slots[i];
-            nslots = 15;
-        }
-        s = &slots[nslots++];
-        *s = Slot{dev, st, nullptr, 0};
-    }
-    if (s->bytes < bytes) {
-        if (s->p) { cudaStreamSynchronize(st); cudaFree(s->p); s->p = nullptr; s->bytes = 0; }
-        const size_t want = bytes + bytes / 8;
-        if (cudaMalloc((void **)&s->p, want) != cudaSuccess) { s->p = nullptr; return nullptr; }
-        s->bytes = want;
-    }
-    return s->p;
+// Workspace of the split path: the kernels of a call hand (d, e, tau, mean, packed reflectors, trailing matrices) from one
+// to the next through `ws`, 12-37 KB per (group, channel) problem.  The CALLER owns it (vnlb_bayes_workspace_bytes);
+// a call with more groups than the workspace holds is processed in stream-ordered chunks.
+constexpr int SPLIT_CHUNK = 16384;                 // groups per chunk at most (a round of the throughput schedule)
+static size_t split_bytes_per_group(const TriLayout &L, int c) {
+    const int stride = L.gram ? gram_ws_stride<60>(L.LD) : split_ws_stride<98>();
+    return (size_t)c * stride * sizeof(float);
+}
+size_t bayes_workspace_bytes(int B, const VnlbBayesParams *p) {
+    const int pd = p->pt * p->ps * p->ps;
+    if (B <= 0 || pd < 3 || pd > TT || p->k < 1 || p->c < 1) return 0;
+    const TriLayout L = tri_layout(p->k, pd);
+    if (!use_split(L)) return 0;
+    return (size_t)(B < SPLIT_CHUNK ? B : SPLIT_CHUNK) * split_bytes_per_group(L, p->c);
 }
 
 template <bool FUSED>
 static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_t st);
 
-// The split path needs a workspace of 12-37 KB per (group, channel) problem: calls with more groups than a round of the
-// throughput schedule are processed in chunks of 16384 groups (1.8 GB of workspace), stream-ordered.
 template <bool FUSED>
-static int launch_bayes_any(BayesArgs &a, int B, const char *what, cudaStream_t st) {
-    constexpr int CHUNK = 16384;
-    if (B <= CHUNK || !use_split(a.L)) return launch_bayes_chunk<FUSED>(a, B, what, st);
+static int launch_bayes_any(BayesArgs &a, int B, const char *what, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!use_split(a.L)) return launch_bayes_chunk<FUSED>(a, B, what, st);
     const VnlbBayesParams &P = a.P;
+    const size_t per_group = split_bytes_per_group(a.L, P.c);
+    long long chunk = ws ? (long long)(ws_bytes / per_group) : 0;
+    if (chunk > SPLIT_CHUNK) chunk = SPLIT_CHUNK;
+    if (chunk < 1 || ((uintptr_t)ws & 15)) {
+        set_error("%s: workspace missing, misaligned or smaller than one group (%zu B per group; see vnlb_bayes_workspace_bytes)",
+                  what, per_group);
+        return VNLB_ERR_WORKSPACE;
+    }
+    a.ws = (float *)ws;
+    a.ws_stride = (int)(per_group / sizeof(float) / P.c);
     const long long rstride = (long long)P.pt * P.c * P.ps * P.ps, gstride = (long long)P.k * rstride;
-    for (int g0 = 0; g0 < B; g0 += CHUNK) {
+    for (int g0 = 0; g0 < B; g0 += (int)chunk) {
         BayesArgs c = a;
         if (c.pnoisy) c.pnoisy += g0 * gstride;
         if (c.pbasic) c.pbasic += g0 * gstride;
         if (c.flat) c.flat += g0;
         if (c.inds) c.inds += (long long)g0 * P.k;
         if (c.rank_var) c.rank_var += g0;
-        const int rc = launch_bayes_chunk<FUSED>(c, B - g0 < CHUNK ? B - g0 : CHUNK, what, st);
+        if (c.dbg_mat) c.dbg_mat += (size_t)g0 * P.c * a.L.q * a.L.q;
+        if (c.dbg_lam) c.dbg_lam += (size_t)g0 * P.c * MR;
+        if (c.dbg_coef) c.dbg_coef += (size_t)g0 * P.c * MR;
+        if (c.dbg_m) c.dbg_m += (size_t)g0 * P.c;
+        const int rc = launch_bayes_chunk<FUSED>(c, B - g0 < chunk ? B - g0 : (int)chunk, what, st);
         if (rc != VNLB_OK) return rc;
     }
     return VNLB_OK;
@@ -2034,13 +1816,7 @@ template <bool FUSED>
 static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_t st) {
     const VnlbBayesParams *p = &a.P;
     cudaError_t e;
-    // the split path needs device memory for its workspace; if that cannot be had, the single-kernel path still works
-    bool split = use_split(a.L);
-    if (split) {
-        a.ws_stride = a.L.gram ? gram_ws_stride<60>(a.L.LD) : split_ws_stride<98>();
-        a.ws = split_workspace((size_t)B * p->c * a.ws_stride * sizeof(float), st);
-        if (!a.ws) { (void)cudaGetLastError(); split = false; }
-    }
+    const bool split = use_split(a.L);                   // a.ws / a.ws_stride were set by launch_bayes_any
     if (split && a.L.gram) {
         constexpr int QD = 60;
         a.ws_pitch = GRAM_PITCH;
@@ -2085,9 +1861,7 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
         k1<<<B * p->c, TT, smem1, st>>>(a);
-        const bool frag = g_split == 2;                     // vnlb_set_bayes_split(2): experimental tensor-core version of the 64 -> 32 phase
-        if (frag) tridiag_tail_frag_kernel<QD, LDG, 4 * LDG, split_trail_off<QD>(), split_trail2_off<QD>()><<<B * p->c, 64, smem1b + 512 * sizeof(float), st>>>(a);
-        else k1b<<<B * p->c, 64, smem1b, st>>>(a);
+        k1b<<<B * p->c, 64, smem1b, st>>>(a);
         k1c<<<B * p->c, 32, smem1c, st>>>(a);
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
         return check_launch(what, 4);
@@ -2107,24 +1881,32 @@ bool bayes_tridiag_supported(const VnlbBayesParams *p) {
     return (size_t)L.total * sizeof(float) <= 227 * 1024 && ((L.LDq >> 2) * ((L.LDq >> 2) + 1) / 2) <= 3 * TT;
 }
 
+int bayes_matrix_dim(const VnlbBayesParams *p, int *is_gram) {
+    const TriLayout L = tri_layout(p->k, p->pt * p->ps * p->ps);
+    if (is_gram) *is_gram = L.gram;
+    return L.q;
+}
+
 int launch_bayes_tridiag(float *pnoisy, const float *pbasic, const unsigned char *flat, const long long *inds, int B,
-                         const VnlbBayesParams *p, float *rank_var, cudaStream_t st) {
+                         const VnlbBayesParams *p, float *rank_var, void *ws, size_t ws_bytes, cudaStream_t st,
+                         float *dbg_mat, float *dbg_lam, float *dbg_coef, int *dbg_m) {
     BayesArgs a = {};
     a.pnoisy = pnoisy; a.pbasic = pbasic; a.flat = flat; a.inds = inds; a.rank_var = rank_var;
+    a.dbg_mat = dbg_mat; a.dbg_lam = dbg_lam; a.dbg_coef = dbg_coef; a.dbg_m = dbg_m;
     a.P = *p;
     a.L = tri_layout(p->k, p->pt * p->ps * p->ps);
-    return launch_bayes_any<false>(a, B, "vnlb_bayes_filter(tridiag)", st);
+    return launch_bayes_any<false>(a, B, "vnlb_bayes_filter(tridiag)", ws, ws_bytes, st);
 }
 
 int launch_bayes_fused(const float *img_noisy, const float *img_basic, const long long *inds, int B, int T, int H,
                        int W, const VnlbBayesParams *p, float flat_thresh, float *deno, float *weights,
-                       cudaStream_t st) {
+                       void *ws, size_t ws_bytes, cudaStream_t st) {
     BayesArgs a = {};
     a.img_noisy = img_noisy; a.img_basic = img_basic; a.inds = inds; a.deno = deno; a.weights = weights;
     a.T = T; a.H = H; a.W = W; a.flat_thresh = flat_thresh;
     a.P = *p;
     a.L = tri_layout(p->k, p->pt * p->ps * p->ps);
-    return launch_bayes_any<true>(a, B, "vnlb_bayes_aggregate_fused", st);
+    return launch_bayes_any<true>(a, B, "vnlb_bayes_aggregate_fused", ws, ws_bytes, st);
 }
 
 }  // namespace vnlb

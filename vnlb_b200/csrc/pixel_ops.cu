@@ -75,16 +75,19 @@ __global__ void normalize_kernel(float *__restrict__ deno, const float *__restri
 }
 
 // mask.py:315-358 restated as a per-pixel predicate (whole-frame case)
+// Tiles (multi-GPU): the buffer holds rows [y_off, y_off + H) of a frame of H_total rows; the lattice phase, the
+// "first / last row" rule and the valid range follow the GLOBAL row hi = y_off + local row; y_begin / y_end are local.
 __global__ void init_mask_kernel(int8_t *__restrict__ mask, int T, int H, int W, int end_t, int end_h,
-                                 int end_w, int step, int y_begin, int y_end) {
+                                 int end_w, int step, int y_begin, int y_end, int y_off, int ps) {
     const long long n = (long long)T * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         const int wi = (int)(i % W);
-        const int hi = (int)((i / W) % H);
+        const int hl = (int)((i / W) % H);
+        const int hi = hl + y_off;
         const int ti = (int)(i / ((long long)W * H));
         bool set = false;
-        if (ti < end_t && hi < end_h && wi < end_w && hi >= y_begin && hi < y_end) {
+        if (ti < end_t && hi < end_h && wi < end_w && hl >= y_begin && hl < y_end && hl + ps <= H) {
             const bool last_t = ti == end_t - 1;
             const int phase_h = last_t ? 0 : ti;
             const bool last_h = hi == end_h - 1;
@@ -174,9 +177,69 @@ __global__ void pad_queries_kernel(long long *__restrict__ qinds, const unsigned
         if ((unsigned)i >= n) { qinds[3 * (long long)i] = -1; qinds[3 * (long long)i + 1] = -1; qinds[3 * (long long)i + 2] = -1; }
 }
 
+// ---------------------------------------------------------------------------
+// throughput schedule: greedy conflict resolution INSIDE a round.  The reference processes its reference pixels
+// sequentially in sub-batches of 128 and every sub-batch clears what it found before the next one is drawn
+// (search.py:38-64), so a pixel covered by an earlier group is never processed.  A round of this schedule draws
+// thousands of pixels at once; without this step two drawn pixels that cover each other are both processed
+// (+9..13 % groups, profiles/r1b).  Pass 1: every valid row i stamps owner[pixel] = min(owner, key(round, i)) at
+// each pixel its group would clear (found patches + the 4 boost neighbours).  Pass 2: row j is dropped (its
+// indices set to -1) when the stamp on its own reference pixel comes from a row i < j of the same round; its pixel
+// goes back into the mask, so if the group that covered it is dropped as well it is drawn again in a later round.
+// key = (65535 - round) << 15 | row: later rounds always win the atomicMin over stale stamps, no clearing needed.
+// ---------------------------------------------------------------------------
+__global__ void round_stamp_kernel(const long long *__restrict__ inds, int K, unsigned int *__restrict__ owner,
+                                   unsigned int round_key, int T, int C, int H, int W, int boost) {
+    const long long *row = inds + (long long)blockIdx.x * K;
+    if (!row_valid_block(row, K)) return;
+    const unsigned int key = round_key | blockIdx.x;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        int t, y, x;
+        decode_ind(row[i], H, W, C, t, y, x);
+        if (t < 0 || t >= T) continue;
+        unsigned int *o = owner + (long long)t * H * W;
+        atomicMin(o + (long long)y * W + x, key);
+        if (boost) {
+            if (x > 0) atomicMin(o + (long long)y * W + x - 1, key);
+            if (x < W - 1) atomicMin(o + (long long)y * W + x + 1, key);
+            if (y < H - 1) atomicMin(o + (long long)(y + 1) * W + x, key);
+            if (y > 0) atomicMin(o + (long long)(y - 1) * W + x, key);
+        }
+    }
+}
+
+__global__ void round_drop_kernel(const long long *__restrict__ qinds, long long *__restrict__ inds, int B, int K,
+                                  const unsigned int *__restrict__ owner, unsigned int round_key,
+                                  int8_t *__restrict__ mask, int T, int H, int W, unsigned int *__restrict__ dropped) {
+    const int j = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= B) return;
+    const long long t = qinds[3 * (long long)j], y = qinds[3 * (long long)j + 1], x = qinds[3 * (long long)j + 2];
+    if (t < 0 || t >= T || y < 0 || y >= H || x < 0 || x >= W) return;
+    const long long pix = (t * H + y) * W + x;
+    const unsigned int o = owner[pix];
+    if ((o & ~0x7fffu) != round_key || (o & 0x7fffu) >= (unsigned)j) return;   // not covered by an earlier row of this round
+    long long *row = inds + (long long)j * K;
+    if (row[0] < 0) return;                                                     // already invalid
+    for (int i = lane; i < K; i += 32) row[i] = -1;
+    if (lane == 0) { mask[pix] = 1; atomicAdd(dropped, 1u); }
+}
+
 }  // namespace vnlb
 
 using namespace vnlb;
+
+extern "C" int vnlb_round_dedup(const int64_t *qinds, int64_t *inds, int B, int K, uint32_t *owner, uint32_t round,
+                                int8_t *mask, int T, int C, int H, int W, int boost, uint32_t *dropped, void *stream) {
+    VNLB_REQUIRE(qinds && inds && owner && mask && dropped && B >= 0 && K > 0, "vnlb_round_dedup: bad argument");
+    VNLB_REQUIRE(T > 0 && C > 0 && H > 0 && W > 0, "vnlb_round_dedup: bad shape");
+    VNLB_REQUIRE(B <= 32768 && round < 65535u, "vnlb_round_dedup: at most 32768 rows per round and 65535 rounds");
+    if (B == 0) return VNLB_OK;
+    const unsigned int key = (65535u - round) << 15;
+    round_stamp_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const long long *)inds, K, owner, key, T, C, H, W, boost);
+    round_drop_kernel<<<div_up(B, 8), 256, 0, (cudaStream_t)stream>>>((const long long *)qinds, (long long *)inds, B, K,
+                                                                     owner, key, mask, T, H, W, dropped);
+    return check_launch("vnlb_round_dedup", 2);
+}
 
 extern "C" const char *vnlb_last_error(void) { return g_err; }
 extern "C" int vnlb_version(void) { return 101; }
@@ -213,15 +276,22 @@ extern "C" int vnlb_normalize(float *deno, const float *weights, const float *fi
     return check_launch("vnlb_normalize");
 }
 
-extern "C" int vnlb_init_mask(int8_t *mask, int T, int H, int W, int ps, int pt, int proc_step, int y_begin,
-                              int y_end, void *stream) {
+extern "C" int vnlb_init_mask_tile(int8_t *mask, int T, int H, int W, int ps, int pt, int proc_step, int y_begin,
+                                   int y_end, int y_offset, int H_total, void *stream) {
     VNLB_REQUIRE(mask && T > 0 && H > 0 && W > 0, "vnlb_init_mask: bad argument");
     VNLB_REQUIRE(ps >= 1 && pt >= 1 && proc_step >= 1, "vnlb_init_mask: bad patch size / step");
     VNLB_REQUIRE(T >= pt && H >= ps && W >= ps, "vnlb_init_mask: video smaller than one patch");
+    VNLB_REQUIRE(y_offset >= 0 && y_offset + H <= H_total, "vnlb_init_mask: tile rows [%d, %d) outside the frame of %d rows",
+                 y_offset, y_offset + H, H_total);
     const long long n = (long long)T * H * W;
-    init_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, T, H, W, T - pt + 1, H - ps + 1,
-                                                                        W - ps + 1, proc_step, y_begin, y_end);
+    init_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mask, T, H, W, T - pt + 1, H_total - ps + 1,
+                                                                        W - ps + 1, proc_step, y_begin, y_end, y_offset, ps);
     return check_launch("vnlb_init_mask");
+}
+
+extern "C" int vnlb_init_mask(int8_t *mask, int T, int H, int W, int ps, int pt, int proc_step, int y_begin,
+                              int y_end, void *stream) {
+    return vnlb_init_mask_tile(mask, T, H, W, ps, pt, proc_step, y_begin, y_end, 0, H, stream);
 }
 
 extern "C" int vnlb_count_mask(const int8_t *mask, int T, int H, int W, uint32_t *counters, void *stream) {

@@ -1,27 +1,39 @@
-"""Multi-GPU VNLB: one process per GPU (torch.distributed, NCCL over NVLink).
+"""Multi-GPU VNLB: one process per GPU (torch.distributed, NCCL over NVLink), the video split into row bands with halos.
 
-The path shards over REFERENCE PIXELS: every rank holds the whole
-video (a 1080p x 30 float32 video is 746 MB, trivial next to 180 GB of HBM) and
-owns one horizontal band of the reference-pixel lattice; it searches, filters
-and aggregates only the groups whose reference pixel lies in its band.  Groups
-of neighbouring bands overlap at the band borders (patches reach a search-window
-radius into the neighbour), so the per-step accumulators (sum image + weights)
-are summed across ranks -- the one collective of the path -- and every rank then
-normalises locally, which also gives each rank the complete `basic` image that
-step 2 searches.  Each rank runs its own greedy mask over its own band, so the
-multi-GPU output matches the single-GPU output within the PSNR tolerance
-(0.02 dB), not max-abs."""
+The path shards over REFERENCE PIXELS (BASELINE north star): rank r owns one contiguous band
+[y0_r, y1_r) of reference rows and holds only the row TILE [y0_r - halo, y1_r + halo) of the video (and of the
+flows) in HBM -- the rows its search windows and patches can reach:
+
+    halo = w_s // 2 + ps - 1 + ceil(nWt * (max|flow_y| + 0.5))      (19 rows for the default parameters, zero flow)
+
+so each rank copies (band + 2 halo) / H of the video host -> device, runs the single-GPU step on its tile (the same
+kernels, tile-local coordinates, the reference-pixel lattice kept in GLOBAL phase by vnlb_init_mask_tile) and
+exchanges, per step, only what overlaps a neighbour:
+
+  1. the accumulator rows (sum image + weights) its groups wrote into rows another rank owns are sent to that
+     rank and added there (neighbour send/recv of T x (C+1) x rows x W floats per border and direction);
+  2. after normalisation the owner returns the normalised rows of step 1 that lie in the neighbour's halo, because
+     step 2 searches and gathers the `basic` estimate over the whole tile.
+
+No other data-path communication: there is no all-reduce of frames.  At the end the bands are gathered so that every
+rank returns the full (deno, basic) like the single-GPU call.  Each rank runs its own greedy mask over its own band,
+so a group found across a band border does not clear the other rank's mask: slightly more groups near the N-1
+borders and an estimate there that differs from the single-GPU one within the PSNR tolerance (0.02 dB), not
+max-abs (caveat H7 of SURVEY.md; tests/test_dist_gpu.py asserts it)."""
+import math
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import alloc
+from . import alloc, color
 from .params import get_args, get_params
-from .utils import Timer, prepare_flows
+from .utils import AttrDict, Timer, expand_flows
 
 
+# ------------------------------------------------------------------------------------------------ partition (host)
 def partition_rows(h, ps, world_size, rank):
-    """Band [y0, y1) of reference-pixel rows (valid rows are 0..h-ps) of `rank`."""
+    """Band [y0, y1) of reference-pixel rows (valid rows are 0..h-ps) of `rank`: equal row counts."""
     valid = h - ps + 1
     y0 = (valid * rank) // world_size
     y1 = (valid * (rank + 1)) // world_size
@@ -30,101 +42,245 @@ def partition_rows(h, ps, world_size, rank):
     return y0, y1
 
 
-def partition_rows_snake(h, ps, world_size, rank):
-    """Two bands per rank, assigned boustrophedon (rank r owns bands r and 2N-1-r of 2N), so that
-    content that changes from the top to the bottom of the frame is averaged over the ranks:
-    the number of groups a band produces depends on its texture, not only on its size."""
-    if world_size == 1:
-        return [partition_rows(h, ps, 1, 0)]
-    a = partition_rows(h, ps, 2 * world_size, rank)
-    b = partition_rows(h, ps, 2 * world_size, 2 * world_size - 1 - rank)
-    return [a, b]
-
-
 def partition_rows_weighted(weights, ps, world_size, rank):
-    """One contiguous band per rank with (nearly) equal total weight; `weights` [H] = groups per reference
-    row observed in the previous step (identical on every rank).  Fewer band borders than the snake
-    partition and balanced on the actual content."""
-    h = int(weights.shape[0])
+    """One contiguous band per rank with (nearly) equal total weight; `weights` [H] = expected cost per reference
+    row (identical on every rank), e.g. the per-row group counts or device time of an earlier call on similar
+    content.  Bands stay non-empty and ordered."""
+    w = torch.as_tensor(weights).double().flatten()
+    h = int(w.shape[0])
     valid = h - ps + 1
-    w = weights[:valid].double() + 1e-3                    # every row keeps a little weight
+    w = w[:valid] + 1e-3 * float(w[:valid].mean() + 1e-12)     # every row keeps a little weight
     cum = torch.cumsum(w, 0)
     total = float(cum[-1])
     cuts = [0]
     for r in range(1, world_size):
-        cuts.append(int(torch.searchsorted(cum, torch.tensor(total * r / world_size, dtype=cum.dtype,
-                                                             device=cum.device)).item()) + 1)
+        cuts.append(int(torch.searchsorted(cum, torch.tensor(total * r / world_size, dtype=cum.dtype)).item()) + 1)
     cuts.append(h)
-    for r in range(1, world_size + 1):                     # keep the bands non-empty and ordered
+    for r in range(1, world_size + 1):
         cuts[r] = max(cuts[r], cuts[r - 1] + 1) if r < world_size else h
     return cuts[rank], cuts[rank + 1]
 
 
-def allreduce_accumulators(images, group=None):
-    """Sum the aggregation accumulators over ranks (border overlap + band union)."""
-    dist.all_reduce(images.deno, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(images.weights, op=dist.ReduceOp.SUM, group=group)
+def halo_rows(params, max_flow=0.0):
+    """Rows above / below a band of reference pixels that its groups can touch: the search window radius plus the
+    patch extent plus the drift of the flow trajectory over the temporal search range (both steps)."""
+    halo = 0
+    for step in (0, 1):
+        nwt = max(int(params["sizeSearchTimeFwd"][step]), int(params["sizeSearchTimeBwd"][step]))
+        drift = int(math.ceil(nwt * (float(max_flow) + 0.5))) if max_flow > 0 else 0
+        halo = max(halo, int(params["sizeSearchWindow"][step]) // 2 + int(params["sizePatch"][step]) - 1 + drift)
+    return halo
 
 
-def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="default", params=None,
-                        stats=None, group=None, device=None, clean=None, balance=True):
-    """vnlb.denoise over all ranks of `group`.  Every rank passes the same `noisy`
-    (host or device) and receives the full (deno, basic, seconds).
+def make_layout(h, ps, world_size, halo, row_weights=None):
+    """bands[r] = (y0, y1) reference rows owned by rank r, tiles[r] = (ya, yb) rows rank r holds; global rows."""
+    if row_weights is None:
+        bands = [partition_rows(h, ps, world_size, r) for r in range(world_size)]
+    else:
+        bands = [partition_rows_weighted(row_weights, ps, world_size, r) for r in range(world_size)]
+    tiles = [(max(0, a - halo), min(h, b + halo)) for a, b in bands]
+    return bands, tiles
 
-    balance: True / "snake" = two boustrophedon bands per rank in both steps (default; measured best at
-    N = 8: 394.6 ms per call); "weighted" = step-2 bands equalised on the step-1 group histogram
-    (measured worse: 405.4 ms -- the cost of a group in step 2 depends on its content, not only on the
-    count); False = one plain band per rank."""
+
+def _overlap(a, b):
+    lo, hi = max(a[0], b[0]), min(a[1], b[1])
+    return (lo, hi) if hi > lo else None
+
+
+def exchange_plan(bands, tiles, rank):
+    """Row ranges (global) this rank exchanges with every other rank:
+    give[s] = rows of MY tile that rank s owns (my accumulations there go to s; s's normalised rows come back),
+    take[s] = rows of s's tile that I own      (s's accumulations come to me; my normalised rows go to s)."""
+    give, take = {}, {}
+    for s in range(len(bands)):
+        if s == rank:
+            continue
+        g = _overlap(tiles[rank], bands[s])
+        t = _overlap(tiles[s], bands[rank])
+        if g:
+            give[s] = g
+        if t:
+            take[s] = t
+    return give, take
+
+
+# ------------------------------------------------------------------------------------------------ exchanges
+def _p2p(sends, recvs, group):
+    """sends / recvs: lists of (tensor, peer).  One batched isend/irecv (NCCL groups it; gloo runs it pairwise)."""
+    ops = [dist.P2POp(dist.irecv, t, dist.get_global_rank(group, p) if group is not None else p, group) for t, p in recvs]
+    ops += [dist.P2POp(dist.isend, t, dist.get_global_rank(group, p) if group is not None else p, group) for t, p in sends]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def exchange_accumulators(deno, weights, ya, give, take, group=None):
+    """Step 1 of the border exchange: the rows of the tile accumulators (deno [T,C,hb,W], weights [T,hb,W]; tile row 0 =
+    global row ya) that another rank owns are sent there; the contributions of the others to my rows are added."""
+    t, c, hb, w = deno.shape
+    sends, recvs, bufs = [], [], {}
+    for s, (lo, hi) in sorted(give.items()):
+        buf = torch.empty((t, c + 1, hi - lo, w), dtype=deno.dtype, device=deno.device)
+        buf[:, :c] = deno[:, :, lo - ya:hi - ya]
+        buf[:, c] = weights[:, lo - ya:hi - ya]
+        sends.append((buf, s))
+    for s, (lo, hi) in sorted(take.items()):
+        bufs[s] = torch.empty((t, c + 1, hi - lo, w), dtype=deno.dtype, device=deno.device)
+        recvs.append((bufs[s], s))
+    _p2p(sends, recvs, group)
+    for s, (lo, hi) in sorted(take.items()):
+        deno[:, :, lo - ya:hi - ya] += bufs[s][:, :c]
+        weights[:, lo - ya:hi - ya] += bufs[s][:, c]
+    return sum(b.numel() for b, _ in sends) * 4
+
+
+def exchange_halo(img, ya, give, take, group=None):
+    """Step 2 of the border exchange: my normalised rows that lie in another rank's tile go there, the normalised rows
+    of the others that lie in my tile's halo overwrite my (partial) ones."""
+    sends, recvs, bufs = [], [], {}
+    for s, (lo, hi) in sorted(take.items()):
+        sends.append((img[:, :, lo - ya:hi - ya].contiguous(), s))
+    for s, (lo, hi) in sorted(give.items()):
+        bufs[s] = torch.empty((img.shape[0], img.shape[1], hi - lo, img.shape[3]), dtype=img.dtype, device=img.device)
+        recvs.append((bufs[s], s))
+    _p2p(sends, recvs, group)
+    for s, (lo, hi) in sorted(give.items()):
+        img[:, :, lo - ya:hi - ya] = bufs[s]
+    return sum(b.numel() for b, _ in sends) * 4
+
+
+def gather_bands(img_tile, ya, bands, rank, h, group=None):
+    """Every rank contributes the rows of its band; returns the full [T,C,H,W] image on every rank."""
+    world = len(bands)
+    t, c, _, w = img_tile.shape
+    hmax = max(b - a for a, b in bands)
+    mine = torch.zeros((t, c, hmax, w), dtype=img_tile.dtype, device=img_tile.device)
+    y0, y1 = bands[rank]
+    mine[:, :, :y1 - y0] = img_tile[:, :, y0 - ya:y1 - ya]
+    allb = torch.empty((world * t, c, hmax, w), dtype=img_tile.dtype, device=img_tile.device)
+    dist.all_gather_into_tensor(allb, mine, group=group)
+    allb = allb.view(world, t, c, hmax, w)
+    full = torch.empty((t, c, h, w), dtype=img_tile.dtype, device=img_tile.device)
+    for r, (a, b) in enumerate(bands):
+        full[:, :, a:b] = allb[r, :, :, :b - a]
+    return full
+
+
+# ------------------------------------------------------------------------------------------------ inputs
+def _rows_to_device(x, ya, yb, device):
+    """Rows [ya, yb) of a [T,C,H,W] host (numpy / torch, ideally pinned) or device array as a contiguous float32 device
+    tensor.  Host input: one async copy per (t, c) plane -- only these rows cross PCIe."""
+    if not torch.is_tensor(x):
+        x = torch.from_numpy(np.asarray(x))
+    if x.is_cuda:
+        return x[:, :, ya:yb].to(device=device, dtype=torch.float32).contiguous()
+    t, c, h, w = x.shape
+    if x.dtype != torch.float32:
+        return x[:, :, ya:yb].to(torch.float32).contiguous().to(device)
+    out = torch.empty((t, c, yb - ya, w), dtype=torch.float32, device=device)
+    if x.is_contiguous():
+        for ti in range(t):
+            for ci in range(c):
+                out[ti, ci].copy_(x[ti, ci, ya:yb], non_blocking=True)
+    else:
+        out.copy_(x[:, :, ya:yb])
+    return out
+
+
+def _max_flow_y(flows, y0, y1):
+    """max |dy| over the rows of this rank's band (host or device tensors)."""
+    m = 0.0
+    for key in ("fflow", "bflow"):
+        f = flows[key]
+        f = f if torch.is_tensor(f) else torch.from_numpy(np.asarray(f))
+        m = max(m, float(f[:, 1, y0:y1].abs().max()))
+    return m
+
+
+def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="default", params=None, stats=None,
+                        group=None, device=None, clean=None, max_flow=None, row_weights=None, gather=True):
+    """vnlb.denoise over all ranks of `group`.  Every rank passes the same `noisy` [T,C,H,W] (host, ideally pinned, or
+    device) and the same `flows`; only its own band + halo rows are copied to its GPU.  Returns (deno, basic, seconds):
+    the full frames on every rank (gather=True) or this rank's band rows only as (deno_band, basic_band, (y0, y1)).
+
+    max_flow : bound on |flow_y| in pixels per frame used to size the halo; None = measured on this rank's band rows
+               (a host pass over them) and agreed over the ranks (max).  The bound is verified on the device.
+    row_weights : optional [H] expected cost per reference row for the band partition (None = equal row counts).
+    """
     clock = Timer()
     clock.tic()
+    if schedule != "fast":
+        raise ValueError("denoise_distributed runs the throughput schedule (the parity schedule replays the reference's "
+                         "single-process random draws and has no multi-GPU meaning)")
+    if clean is not None:
+        raise ValueError("denoise_distributed: `clean` is not used by the default parameters (srch_img) and is not sharded")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-    from .proc_nl import proc_nl
     from .schedule import proc_nl_fast
-    step_fn = proc_nl_fast if schedule == "fast" else proc_nl
+    T, C, H, W = (int(v) for v in noisy.shape)
+    params = params if params is not None else get_params(sigma, False, version)
+    ps = int(params["sizePatch"][0])
     with torch.cuda.device(device):
-        if not torch.is_tensor(noisy):
-            noisy = torch.from_numpy(np.ascontiguousarray(noisy))
-        noisy = noisy.to(device=device, dtype=torch.float32).contiguous()
-        t, c, h, w = noisy.shape
-        params = params if params is not None else get_params(sigma, False, version)
-        dflows = prepare_flows(flows, noisy.shape, device)
+        # ---- layout: band of reference rows, tile = band + halo
+        has_flow = flows is not None and flows.get("fflow") is not None and flows.get("bflow") is not None
+        if has_flow and max_flow is None:
+            y0u, y1u = partition_rows(H, ps, world, rank)
+            mf = torch.tensor([_max_flow_y(flows, y0u, y1u)], device=device)
+            dist.all_reduce(mf, op=dist.ReduceOp.MAX, group=group)
+            max_flow = float(mf.item())
+        halo = halo_rows(params, max_flow if has_flow else 0.0)
+        bands, tiles = make_layout(H, ps, world, halo, row_weights)
+        (y0, y1), (ya, yb) = bands[rank], tiles[rank]
+        give, take = exchange_plan(bands, tiles, rank)
+        # ---- inputs: only the tile's rows are copied to this GPU
+        noisy_t = _rows_to_device(noisy, ya, yb, device)
+        dflows = AttrDict(fflow=None, bflow=None)
+        flow_ok = None
+        if has_flow:
+            ff = _rows_to_device(flows["fflow"], ya, yb, device)
+            bf = _rows_to_device(flows["bflow"], ya, yb, device)
+            ff, bf = expand_flows(dict(fflow=ff, bflow=bf), T)
+            dflows.fflow, dflows.bflow = ff.contiguous(), bf.contiguous()
+            flow_ok = torch.maximum(ff[:, 1].abs().amax(), bf[:, 1].abs().amax()) <= max_flow + 1e-6
+        sent = [0, 0]
+        st = stats if stats is not None else {}
 
         def reduce_fn(images):
-            if stats is None:
-                allreduce_accumulators(images, group)
-                return
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            allreduce_accumulators(images, group)
-            e1.record()
-            stats.setdefault("allreduce_events", []).append((e0, e1))
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if stats is not None else None
+            if ev:
+                ev[0].record()
+            sent[0] += exchange_accumulators(images.deno, images.weights, ya, give, take, group)
+            if ev:
+                ev[1].record()
+                stats.setdefault("exchange_events", []).append(ev)
 
-        basic = None
-        row_hist = None
-        st = stats if stats is not None else {}
-        for step in (0, 1):
-            images = alloc.allocate_images(noisy, basic, clean)
-            args = get_args(params, c, step, device)
-            mode = balance
-            if mode == "auto" or mode is True:
-                mode = "snake"
-            if not mode:
-                y_range = partition_rows(h, args.ps, world, rank)
-            elif step == 1 and row_hist is not None and mode == "weighted":
-                y_range = partition_rows_weighted(row_hist, args.ps, world, rank)     # balanced on step-1 group density
-            else:
-                y_range = partition_rows_snake(h, args.ps, world, rank)
-            st["want_row_hist"] = bool(mode == "weighted" and step == 0 and schedule == "fast")
-            step_fn(images, dflows, args, st, y_range, reduce_fn)
-            if step == 0:
-                basic = images["deno"].clone()
-                if st.get("row_hist") is not None:
-                    row_hist = st.pop("row_hist")
-                    dist.all_reduce(row_hist, op=dist.ReduceOp.SUM, group=group)
-        st.pop("want_row_hist", None)
-        deno = images["deno"]
+        def post_fn(images):
+            sent[1] += exchange_halo(images.deno, ya, give, take, group)
+
+        noisy_yuv = color.rgb2yuv(noisy_t)
+        tile = (ya, H)
+        band_local = (y0 - ya, y1 - ya)
+        images = alloc.allocate_images_lean(noisy_yuv, None, None)
+        proc_nl_fast(images, dflows, get_args(params, C, 0, device), st, band_local, reduce_fn, tile, post_fn)
+        basic_t, basic_yuv = images.deno, images.deno_yuv
+        images = alloc.allocate_images_lean(noisy_yuv, basic_yuv, None)
+        proc_nl_fast(images, dflows, get_args(params, C, 1, device), st, band_local, reduce_fn, tile, None)
+        deno_t = images.deno
+        if gather:
+            deno = gather_bands(deno_t, ya, bands, rank, H, group)
+            basic = gather_bands(basic_t, ya, bands, rank, H, group)
+        else:
+            deno = deno_t[:, :, y0 - ya:y1 - ya].contiguous()
+            basic = basic_t[:, :, y0 - ya:y1 - ya].contiguous()
         torch.cuda.synchronize(device)
-        if stats is not None and "allreduce_events" in stats:
-            stats["allreduce_ms"] = [a.elapsed_time(b) for a, b in stats.pop("allreduce_events")]
-    return deno, basic, clock.toc()
+        if flow_ok is not None and not bool(flow_ok):
+            raise ValueError("denoise_distributed: |flow_y| exceeds max_flow = %g on rank %d; the halo (%d rows) is too small"
+                             % (max_flow, rank, halo))
+        if stats is not None:
+            stats["layout"] = dict(band=(y0, y1), tile=(ya, yb), halo=halo, rows_copied=yb - ya, rows_total=H)
+            stats["exchange_bytes"] = dict(accumulators=sent[0], halo=sent[1])
+            if "exchange_events" in stats:
+                stats["exchange_ms"] = [a.elapsed_time(b) for a, b in stats.pop("exchange_events")]
+    if gather:
+        return deno, basic, clock.toc()
+    return deno, basic, (y0, y1)

@@ -2,7 +2,7 @@
 import numpy as np
 import torch
 
-from . import alloc
+from . import alloc, color
 from .params import get_args, get_params
 from .proc_nl import proc_nl
 from .utils import Timer, prepare_flows
@@ -46,21 +46,30 @@ def denoise(noisy, sigma, gpuid=0, clean=None, verbose=True, flows=None, schedul
         c = noisy.shape[1]
         params = params if params is not None else get_params(sigma, verbose, version)
         dflows = prepare_flows(flows, noisy.shape, device)
-        step_fn = proc_nl
+        from .schedule import proc_nl_fast
+
         if schedule == "fast":
-            from .schedule import proc_nl_fast
-            step_fn = proc_nl_fast
+            # throughput schedule: colour conversion once per call (not once per step and image), no zero images
+            # converted, no clone of the basic estimate
+            noisy_yuv = color.rgb2yuv(noisy)
+            clean_yuv = color.rgb2yuv(clean) if clean is not None else None
+            images = alloc.allocate_images_lean(noisy_yuv, None, clean_yuv)
+            proc_nl_fast(images, dflows, get_args(params, c, 0, device), stats)
+            basic, basic_yuv = images.deno, images.deno_yuv
+            images = alloc.allocate_images_lean(noisy_yuv, basic_yuv, clean_yuv)
+            proc_nl_fast(images, dflows, get_args(params, c, 1, device), stats)
+            deno = images.deno
+        else:
+            # -- [step 1] --
+            images = alloc.allocate_images(noisy, None, clean)
+            args = get_args(params, c, 0, device)
+            proc_nl(images, dflows, args, stats)
+            basic = images["deno"].clone()
 
-        # -- [step 1] --
-        images = alloc.allocate_images(noisy, None, clean)
-        args = get_args(params, c, 0, device)
-        step_fn(images, dflows, args, stats)
-        basic = images["deno"].clone()
-
-        # -- [step 2] --
-        images = alloc.allocate_images(noisy, basic, clean)
-        args = get_args(params, c, 1, device)
-        step_fn(images, dflows, args, stats)
-        deno = images["deno"]
+            # -- [step 2] --
+            images = alloc.allocate_images(noisy, basic, clean)
+            args = get_args(params, c, 1, device)
+            proc_nl(images, dflows, args, stats)
+            deno = images["deno"]
         torch.cuda.synchronize(device)
     return deno, basic, clock.toc()

@@ -17,15 +17,18 @@ def init_mask(shape, args, device=None, y_range=None):
     return mask, int(mask.sum().item())
 
 
-def init_mask_device(shape, args, device, y_range=None):
-    """The mask only (no host sync).  `y_range`: None, (y0, y1) or a list of such bands."""
+def init_mask_device(shape, args, device, y_range=None, tile=None):
+    """The mask only (no host sync).  `y_range`: None, (y0, y1) or a list of such bands (local rows).
+    `tile` = (y_offset, H_total): `shape` is a row tile of a frame of H_total rows starting at global row
+    y_offset (multi-GPU band + halo); the lattice follows the global rows."""
     t, c, h, w = shape
     bands = [(0, h)] if y_range is None else ([y_range] if isinstance(y_range[0], int) else list(y_range))
+    y_off, h_total = (0, h) if tile is None else (int(tile[0]), int(tile[1]))
     mask = None
     for (y0, y1) in bands:
         m = torch.empty((t, h, w), dtype=torch.int8, device=device)
-        L.check(L.lib.vnlb_init_mask(L.ptr(m), t, h, w, args.ps, args.pt, args.procStep, int(y0), int(y1),
-                                     L.stream_ptr()), "vnlb_init_mask")
+        L.check(L.lib.vnlb_init_mask_tile(L.ptr(m), t, h, w, args.ps, args.pt, args.procStep, int(y0), int(y1),
+                                          y_off, h_total, L.stream_ptr()), "vnlb_init_mask_tile")
         mask = m if mask is None else torch.bitwise_or(mask, m)
     return mask
 

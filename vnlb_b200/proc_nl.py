@@ -50,11 +50,19 @@ def proc_nl(images, flows, args, stats=None, y_range=None, reduce_fn=None):
         stats.setdefault("nmask", []).append(nelems)
 
 
-def finish_step(images, args, reduce_fn=None):
-    """proc_nl.py:118-141: normalise, fill holes, back to RGB.  `reduce_fn` (multi-GPU)
-    sums the accumulators across ranks first."""
+def finish_step(images, args, reduce_fn=None, post_fn=None):
+    """proc_nl.py:118-141: normalise, fill holes, back to RGB.  Multi-GPU hooks: `reduce_fn(images)` adds the other
+    ranks' contributions to the accumulators first; `post_fn(images)` runs on the normalised YUV estimate (exchange of
+    the halo rows the next step searches).  Lean image sets (images.is_yuv: the throughput schedule's, whose inputs
+    were converted once by the caller) convert only the estimate back; images.deno_yuv keeps its YUV version."""
     if reduce_fn is not None:
         reduce_fn(images)
     agg.normalize(images, args)
-    color.yuv2rgb_images(images)
-    torch.cuda.synchronize(images.device)
+    if post_fn is not None:
+        post_fn(images)
+    if images.get("is_yuv"):
+        images.deno_yuv = images.deno
+        images.deno = color.yuv2rgb_new(images.deno_yuv)
+    else:
+        color.yuv2rgb_images(images)
+        torch.cuda.synchronize(images.device)

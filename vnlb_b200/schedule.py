@@ -10,8 +10,13 @@ per 128 groups.  Here each round draws, on the device, a hash-random fraction
 `fast_cap` rows), searches them in one launch, clears everything they found
 (paste trick + boost) and then filters/aggregates the round.  Two pixels drawn
 in the same round may cover each other (the reference has the same effect inside
-one sub-batch); a small `fast_frac` keeps that redundancy at a few percent.
-One 8-byte device->host read per round tells the host the round size."""
+one sub-batch of 128): vnlb_round_dedup drops the later one before it is
+filtered, which keeps the number of groups at the reference schedule's level.
+One 8-byte device->host read per round, consumed two rounds late, tells the host
+the round size; the host never waits for the GPU inside the loop."""
+import threading
+from collections import OrderedDict
+
 import torch
 
 from . import _lib as L
@@ -21,107 +26,59 @@ from .flat_areas import update_flat_patch
 from .proc_nl import finish_step
 from .utils import AttrDict
 
-FAST_DEFAULTS = dict(fast_frac=1. / 8, fast_min=4096, fast_cap=16384, fast_seed=123)
+FAST_DEFAULTS = dict(fast_frac=1. / 8, fast_min=4096, fast_cap=16384, fast_seed=123, fast_dedup=True)
 
 
 class _Workspace:
-    """Round buffers, cached per (device, rows, k, pt, c, ps) so both steps and
-    repeated calls reuse them."""
-    _cache = {}
+    """Round buffers, streams and events, cached per (device, rows, k, pt, c, ps) so both steps and repeated calls
+    reuse them (LRU, at most `_max` entries; guarded by a lock).  denoise() is NOT re-entrant per device: two host
+    threads running the fast schedule on the same device at the same time would share these buffers."""
+    _cache = OrderedDict()
+    _lock = threading.Lock()
+    _max = 8
 
     @classmethod
     def get(cls, device, cap, k, pt, c, ps, stacks=True):
         key = (str(device), cap, k, pt, c, ps, stacks)
-        ws = cls._cache.get(key)
-        if ws is None:
-            if len(cls._cache) >= 4:          # both steps (k = 100 / 60) keep their buffers between calls
-                cls._cache.clear()
-            ws = AttrDict()
-            rows = cap if stacks else 0     # the fused kernel never materialises the patch stacks
-            ws.noisy = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
-            ws.basic = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
-            ws.flat = torch.zeros((cap,), dtype=torch.uint8, device=device)
-            # two sets of round buffers: the search of round r+1 overlaps the Bayes kernel of round r
-            ws.vals2 = [torch.empty((cap, k), dtype=torch.float32, device=device) for _ in range(2)]
-            ws.inds2 = [torch.empty((cap, k), dtype=torch.int64, device=device) for _ in range(2)]
-            ws.qinds2 = [torch.empty((cap, 3), dtype=torch.int64, device=device) for _ in range(2)]
-            ws.vals, ws.inds, ws.qinds = ws.vals2[0], ws.inds2[0], ws.qinds2[0]
-            ws.counters4 = torch.zeros((4, 2), dtype=torch.int32, device=device)
-            ws.host4 = torch.zeros((4, 2), dtype=torch.int32).pin_memory()
-            ws.ev_search = [torch.cuda.Event() for _ in range(2)]     # re-used every round (no per-round garbage)
-            ws.ev_bayes = [torch.cuda.Event() for _ in range(2)]
-            ws.ev_copied = [torch.cuda.Event() for _ in range(4)]
-            ws.search_stream = torch.cuda.Stream(device=device)
-            ws.bayes_stream = torch.cuda.Stream(device=device)
-            ws.counters = torch.zeros((2,), dtype=torch.int32, device=device)
-            ws.host = torch.zeros((2,), dtype=torch.int32).pin_memory()
-            cls._cache[key] = ws
+        with cls._lock:
+            ws = cls._cache.get(key)
+            if ws is not None:
+                cls._cache.move_to_end(key)
+                return ws
+            while len(cls._cache) >= cls._max:
+                cls._cache.popitem(last=False)
+            ws = cls._cache[key] = cls._make(device, cap, k, pt, c, ps, stacks)
+            return ws
+
+    @staticmethod
+    def _make(device, cap, k, pt, c, ps, stacks):
+        ws = AttrDict()
+        rows = cap if stacks else 0     # the fused kernel never materialises the patch stacks
+        ws.noisy = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
+        ws.basic = torch.empty((rows, k, pt, c, ps, ps), dtype=torch.float32, device=device)
+        ws.flat = torch.zeros((cap,), dtype=torch.uint8, device=device)
+        # two sets of round buffers: the search of round r+1 overlaps the Bayes kernel of round r
+        ws.vals2 = [torch.empty((cap, k), dtype=torch.float32, device=device) for _ in range(2)]
+        ws.inds2 = [torch.empty((cap, k), dtype=torch.int64, device=device) for _ in range(2)]
+        ws.qinds2 = [torch.empty((cap, 3), dtype=torch.int64, device=device) for _ in range(2)]
+        ws.vals, ws.inds, ws.qinds = ws.vals2[0], ws.inds2[0], ws.qinds2[0]
+        ws.counters4 = torch.zeros((4, 2), dtype=torch.int32, device=device)
+        ws.host4 = torch.zeros((4, 2), dtype=torch.int32).pin_memory()
+        ws.ev_search = [torch.cuda.Event() for _ in range(2)]     # re-used every round (no per-round garbage)
+        ws.ev_bayes = [torch.cuda.Event() for _ in range(2)]
+        ws.ev_copied = [torch.cuda.Event() for _ in range(4)]
+        ws.search_stream = torch.cuda.Stream(device=device)
+        ws.bayes_stream = torch.cuda.Stream(device=device)
+        ws.dropped = torch.zeros((1,), dtype=torch.int32, device=device)
+        ws.counters = torch.zeros((2,), dtype=torch.int32, device=device)
+        ws.host = torch.zeros((2,), dtype=torch.int32).pin_memory()
         return ws
 
 
-def _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed):
-    """The rounds of one step on two streams: [count, draw, search, clear mask] of round r+1 runs on
-    the search stream while the fused Bayes kernel of round r runs on the Bayes stream (the mask only
-    depends on the search results, never on the filtered patches)."""
-    t, c, h, w = images.shape
-    main = torch.cuda.current_stream()
-    sA, sB = ws.search_stream, ws.bayes_stream
-    sA.wait_stream(main)
-    sB.wait_stream(main)
-    done_search = [None, None]      # event: inds2[b] written and mask updated
-    done_bayes = [None, None]       # event: inds2[b] consumed
-    nproc, nrounds, nmask0, buf = 0, 0, None, 0
-    tm = L.timer
-    while True:
-        with torch.cuda.stream(sA):
-            st = L.stream_ptr()
-            ws.counters.zero_()
-            L.check(L.lib.vnlb_count_mask(L.ptr(mask), t, h, w, L.ptr(ws.counters), st), "vnlb_count_mask")
-            ws.host.copy_(ws.counters, non_blocking=True)
-            sA.synchronize()
-            remaining = int(ws.host[0])
-            if nmask0 is None:
-                nmask0 = remaining
-                qmin = min(qmin, max(296, nmask0 // 64))     # small videos: small rounds keep the greedy mask effective
-            if remaining == 0:
-                break
-            target = min(cap, max(qmin, int(remaining * frac)))
-            prob = 1.0 if remaining <= target else target / remaining * 0.97   # stay under cap
-            if done_bayes[buf] is not None:
-                sA.wait_event(done_bayes[buf])                               # round r-2 is done with this buffer
-            qinds, vals, inds = ws.qinds2[buf], ws.vals2[buf], ws.inds2[buf]
-            L.check(L.lib.vnlb_select_queries(L.ptr(mask), t, h, w, prob, seed, nrounds, L.ptr(qinds), cap,
-                                              L.ptr(ws.counters), st), "vnlb_select_queries")
-            ws.host.copy_(ws.counters, non_blocking=True)
-            sA.synchronize()
-            q = min(int(ws.host[1]), cap)
-            nrounds += 1
-            if q == 0:
-                continue
-            tok = tm.start("search_s%d" % args.step) if tm else None
-            search.exec_sim_search_burst(srch_img, qinds[:q], vals[:q], inds[:q], flows, args.sigma, args)
-            if tm:
-                tm.stop(tok)
-            search_mask.update_mask_inds(mask, inds[:q], c, boost=args.aggreBoost)
-            done_search[buf] = torch.cuda.Event()
-            done_search[buf].record(sA)
-        with torch.cuda.stream(sB):
-            sB.wait_event(done_search[buf])
-            tok = tm.start("bayes_s%d" % args.step) if tm else None
-            deno.bayes_aggregate_fused(images, inds[:q], args)
-            if tm:
-                tm.stop(tok)
-            done_bayes[buf] = torch.cuda.Event()
-            done_bayes[buf].record(sB)
-        nproc += q
-        buf ^= 1
-    main.wait_stream(sA)
-    main.wait_stream(sB)
-    return nproc, nrounds, nmask0
-
-
 def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed, est_mask, row_hist=None):
-    """Like _rounds_overlapped, but the host never waits for the GPU inside the loop: every kernel of a
+    """The rounds of one step on two streams: [count, draw, search, clear mask] of round r+1 runs on the search
+    stream while the fused Bayes kernels of round r run on the Bayes stream (the mask only depends on the search
+    results, never on the filtered patches).  The host never waits for the GPU inside the loop: every kernel of a
     round is enqueued with `cap` rows (rows beyond the number actually drawn are padded to invalid queries
     and skipped on the device), the round size is read back two rounds late from a ring of pinned counters,
     and the draw probability is computed from that (stale, hence conservative) count.  The loop ends when a
@@ -129,6 +86,11 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
     t, c, h, w = images.shape
     main = torch.cuda.current_stream()
     sA, sB = ws.search_stream, ws.bayes_stream
+    # greedy conflict resolution inside a round (vnlb_round_dedup): a drawn pixel that an earlier row of the same round
+    # covers is not processed, as in the reference's sequential sub-batches
+    dedup = bool(args.get("fast_dedup", FAST_DEFAULTS["fast_dedup"]))
+    owner = torch.full((t, h, w), -1, dtype=torch.int32, device=images.device) if dedup else None
+    ws.dropped.zero_()
     sA.wait_stream(main)
     sB.wait_stream(main)
     done_search, done_bayes, copied = ws.ev_search, ws.ev_bayes, ws.ev_copied
@@ -168,6 +130,10 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
             search.exec_sim_search_burst(srch_img, qinds, vals, inds, flows, args.sigma, args)
             if tm:
                 tm.stop(tok)
+            if dedup:
+                L.check(L.lib.vnlb_round_dedup(L.ptr(qinds), L.ptr(inds), rows, int(inds.shape[1]), L.ptr(owner), r,
+                                               L.ptr(mask), t, c, h, w, int(bool(args.aggreBoost)), L.ptr(ws.dropped), st),
+                        "vnlb_round_dedup")
             search_mask.update_mask_inds(mask, inds, c, boost=args.aggreBoost)
             done_search[buf].record(sA)
         with torch.cuda.stream(sB):
@@ -196,11 +162,13 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
     nproc += min(int(ws.host4[last][1]), rows_of[last])
     main.wait_stream(sA)
     main.wait_stream(sB)
-    return nproc, nrounds, nmask0
+    ndrop = int(ws.dropped.item()) if dedup else 0          # (end of the step: the one host sync of the loop)
+    return nproc - ndrop, nrounds, nmask0, ndrop
 
 
-def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
-    """One VNLB step with the throughput schedule (same contract as proc_nl)."""
+def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None, tile=None, post_fn=None):
+    """One VNLB step with the throughput schedule (same contract as proc_nl).  `y_range` / `tile`: multi-GPU band of
+    reference rows and position of this row tile in the frame (mask.init_mask_device)."""
     dev = images.device
     t, c, h, w = images.shape
     frac = float(args.get("fast_frac", FAST_DEFAULTS["fast_frac"]))
@@ -208,35 +176,36 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
     cap = int(args.get("fast_cap", FAST_DEFAULTS["fast_cap"]))
     seed = int(args.get("fast_seed", FAST_DEFAULTS["fast_seed"])) + 7919 * int(args.step)
     k = args.npatches
-    fused = bool(args.get("fused", True)) and deno.fused_supported(args, c)
+    # the fused kernel keeps 32-bit image offsets and needs its patch shape; anything else runs the staged operators
+    fused = bool(args.get("fused", True)) and deno.fused_supported(args, c, images.shape)
     ws = _Workspace.get(dev, cap, k, args.pt, c, args.ps, stacks=not fused)
-    mask = search_mask.init_mask_device(images.shape, args, dev, y_range)
+    mask = search_mask.init_mask_device(images.shape, args, dev, y_range, tile)
     st = L.stream_ptr()
-    color.rgb2yuv_images(images)
+    if not images.get("is_yuv"):
+        color.rgb2yuv_images(images)
     srch_img = {"noisy": images.noisy, "basic": images.basic, "clean": images.clean}[args.srch_img]
     if srch_img is None:
         raise ValueError("uknown search image [%s]" % args.srch_img)
     nproc, nrounds, nmask0 = 0, 0, None
-    overlap = args.get("fast_overlap", "async")
-    if fused and overlap:
-        if overlap == "async":
-            bands = [(0, h)] if y_range is None else ([y_range] if isinstance(y_range[0], int) else list(y_range))
-            rows = sum(min(b, h - args.ps + 1) - a for a, b in bands)
-            est = (t - args.pt + 1) * max(rows, 1) * (w - args.ps + 1) // (args.procStep ** 2)
-            row_hist = None
-            if stats is not None and stats.get("want_row_hist"):
-                row_hist = torch.zeros((h,), dtype=torch.float32, device=dev)
-                stats["row_hist"] = row_hist
-            nproc, nrounds, nmask0 = _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed,
-                                                   est + est // 8, row_hist)
-        else:
-            nproc, nrounds, nmask0 = _rounds_overlapped(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed)
-        finish_step(images, args, reduce_fn)
+    if fused and args.get("fast_overlap", "async"):
+        bands = [(0, h)] if y_range is None else ([y_range] if isinstance(y_range[0], int) else list(y_range))
+        rows = sum(min(b, h - args.ps + 1) - a for a, b in bands)
+        est = (t - args.pt + 1) * max(rows, 1) * (w - args.ps + 1) // (args.procStep ** 2)
+        row_hist = None
+        if stats is not None and stats.get("want_row_hist"):
+            row_hist = torch.zeros((h,), dtype=torch.float32, device=dev)
+            stats["row_hist"] = row_hist
+        nproc, nrounds, nmask0, ndrop = _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed,
+                                                      est + est // 8, row_hist)
+        finish_step(images, args, reduce_fn, post_fn)
         if stats is not None:
+            stats.setdefault("ndropped", []).append(ndrop)
             stats.setdefault("ngroups", []).append(nproc)
             stats.setdefault("nmask", []).append(nmask0)
             stats.setdefault("nrounds", []).append(nrounds)
         return
+    if images.basic is None:            # staged operators gather the (all-zero) basic image in step 1 like the reference
+        images.basic = torch.zeros_like(images.noisy)
     while True:
         ws.counters.zero_()
         L.check(L.lib.vnlb_count_mask(L.ptr(mask), t, h, w, L.ptr(ws.counters), st), "vnlb_count_mask")
@@ -291,7 +260,7 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None):
         if tm:
             tm.stop(tok)
         nproc += q
-    finish_step(images, args, reduce_fn)
+    finish_step(images, args, reduce_fn, post_fn)
     if stats is not None:
         stats.setdefault("ngroups", []).append(nproc)
         stats.setdefault("nmask", []).append(nmask0)

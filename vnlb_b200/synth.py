@@ -1,13 +1,17 @@
 """Seeded synthetic video for benchmarks and smoke runs (no datasets offline):
 smooth low-frequency field + textured rectangles translating 0-2 px/frame,
-range 0..255, float32 [T,C,H,W]; noisy = clean + N(0, sigma^2), unclipped."""
+range 0..255, float32 [T,C,H,W]; noisy = clean + N(0, sigma^2), unclipped.
+return_flows=True also returns the analytic forward / backward flows [T,2,H,W] (channel 0 = dx, 1 = dy; the objects'
+translations, zero on the background)."""
 import numpy as np
 
 
-def synth_video(T, H, W, seed=123, C=3):
+def synth_video(T, H, W, seed=123, C=3, return_flows=False):
     rng = np.random.RandomState(seed)
     yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
     vid = np.zeros((T, C, H, W), np.float32)
+    ff = np.zeros((T, 2, H, W), np.float32) if return_flows else None
+    bf = np.zeros((T, 2, H, W), np.float32) if return_flows else None
     rects = []
     for _ in range(6):
         rh, rw = rng.randint(H // 6 + 2, H // 2 + 3), rng.randint(W // 6 + 2, W // 2 + 3)
@@ -26,7 +30,13 @@ def synth_video(T, H, W, seed=123, C=3):
             ye, xe = min(H, ya + rh), min(W, xa + rw)
             if ye > ys and xe > xs:
                 vid[t, :, ys:ye, xs:xe] = tex[:, ys - ya:ye - ya, xs - xa:xe - xa]
-    return np.clip(vid, 0, 255).astype(np.float32)
+                if return_flows:     # the object's own translation (the last-drawn object wins, as in the frame)
+                    ff[t, 0, ys:ye, xs:xe], ff[t, 1, ys:ye, xs:xe] = vx, vy
+                    bf[t, 0, ys:ye, xs:xe], bf[t, 1, ys:ye, xs:xe] = -vx, -vy
+    vid = np.clip(vid, 0, 255).astype(np.float32)
+    if return_flows:     # "precomputed flows" of SURVEY 8d: the generator's analytic translation field, |flow| <= 2 px/frame
+        return vid, dict(fflow=ff, bflow=bf)
+    return vid
 
 
 def add_noise(clean, sigma, seed=123):
