@@ -2,23 +2,21 @@
 """bench.py -- vnlb.denoise throughput (steps 1+2) in Mpx/s on synthetic video.
 
     python bench.py --gpus N --steps K --warmup W            # this implementation
-    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle port, all host cores)
 
-Workload: BASELINE.json configs[1] -- 854x480 DAVIS-shaped synthetic RGB, 20
-frames, sigma=20, no flow -- on one GPU.  With N GPUs the video is N bands of
-480 rows stacked vertically (854 x 480N x 20; N=8 is 65.6 Mpx, the size of
-configs[4]); each rank owns one band of reference pixels, so per-GPU work is
-fixed ("weak" scaling) and the accumulators are summed with one all-reduce per
-step.  A "step" of this bench = one full vnlb.denoise call (VNLB steps 1+2).
+Workload (every N): BASELINE.json configs[4] -- ONE fixed 1920x1080 synthetic RGB video of 30 frames with the
+generator's analytic ("precomputed") flows, sigma = 10 as `value` and sigma = 50 as `sigma50`; with N GPUs the SAME
+video is split into N row bands with halos (vnlb_b200/dist.py), i.e. strong scaling.  A "step" of this bench = one full
+vnlb.denoise call (VNLB steps 1+2).  At N = 1 the line also carries the other BASELINE configurations measured in the
+same run (configs[1] 854x480x20, configs[2] search microbench, configs[3] Bayes microbench, configs[0] 64x64x3 on the
+CPU) and the PSNR of the benched (throughput) schedule against the reference-exact schedule and the CPU oracle.
 
-One JSON line is printed by rank 0 (see README / DESIGN.md for the keys).
+One JSON line is printed by rank 0 (see README / DESIGN.md section 7 for the keys).
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -27,26 +25,44 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "vnlb.denoise Mpx/s (steps 1+2)"
-SIGMA = 20.0
-BASE = dict(T=20, H=480, W=854)
-CPU_SAMPLE = dict(T=6, H=96, W=128)
-# multi-GPU band partition (vnlb_b200/dist.py): "auto" (default), "snake", "plain" or "weighted"; override for experiments only
-BALANCE = {"plain": False, "snake": "snake", "weighted": "weighted", "auto": "auto"}[os.environ.get("VNLB_BALANCE", "auto")]
+WORK = dict(T=30, H=1080, W=1920)           # BASELINE configs[4]
+SIGMA, SIGMA_ALT = 10.0, 50.0
+MAX_FLOW = 2.0                              # the generator's objects move at most 2 px / frame (vnlb_b200/synth.py)
+CFG2 = dict(T=20, H=480, W=854, sigma=20.0)   # BASELINE configs[1]
+CPU_SAMPLE = dict(T=6, H=96, W=128)         # bounded sample of the workload for the CPU arm (top-left crop, with flows)
+PARITY_SUB = dict(T=10, H=480, W=854)       # sub-video on which the benched schedule is compared with the parity schedule
+WORKLOAD_DESC = ("1920x1080x30 synthetic RGB, sigma=10 (sigma=50 in `sigma50`), precomputed (analytic) flows "
+                 "(BASELINE configs[4]); one fixed video split over the GPUs in row bands + halos")
 
 
 def load_peaks():
+    """(HBM GB/s, kind, FP32 TFLOP/s, kind, file record).  HBM: driver-written MEASURED_PEAKS.json.  FP32 CUDA-core peak:
+    profiles/fp32_peak.json, written by tools/measure_fp32_peak.py (tools/fp32_peak.cu run on a B200); nominal otherwise."""
+    hbm, hbm_kind = 6650.0, "fallback"
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d.get("hbm_gbs", 6650.0)), "measured"
-    return 6650.0, "fallback"
+        hbm, hbm_kind = float(json.load(open(p)).get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    fp32, fp32_kind, rec = 74.4, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz", None
+    p = os.path.join(ROOT, "profiles", "fp32_peak.json")
+    if os.path.exists(p):
+        rec = json.load(open(p))
+        fp32, fp32_kind = float(rec["fp32_tflops"]), "measured (profiles/fp32_peak.json, tools/fp32_peak.cu)"
+    return hbm, hbm_kind, fp32, fp32_kind, rec
+
+
+def load_ncu_traffic():
+    """DRAM bytes per group of the fused Bayes stage (dram__bytes_read.sum + dram__bytes_write.sum of its kernels from one
+    `ncu --set full` capture, divided by the groups of the captured launch), read from the committed summary."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region, read through NVML from the benchmark
-    thread itself right after each step is enqueued/finished (a few microseconds per query).  A background
-    poller (nvidia-smi -lms or an NVML thread) was measured to cause sporadic +50..100 ms stalls of single
-    steps on this box, so no second thread is used."""
+    """SM clock and throttle reasons DURING the timed region, read through NVML from the benchmark thread itself right
+    after kernel launches (a few microseconds per query).  A background poller was measured to cause sporadic
+    +50..100 ms stalls of single steps, so no second thread is used."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
@@ -87,60 +103,81 @@ class ClockSampler:
                     samples=len(self.rows), source="nvml, sampled while the timed steps execute")
 
 
-def make_video(n_gpus):
-    from vnlb_b200 import synth
-    T, H, W = BASE["T"], BASE["H"] * n_gpus, BASE["W"]
-    clean = synth.synth_video(T, H, W, 123)
-    return clean, synth.add_noise(clean, SIGMA, 123)
+# ------------------------------------------------------------------------------------------------ CPU arm
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
-def cpu_reference_run(threads=None):
-    """The reference's CPU implementation of the path (oracle port: the
-    reference's own stages restated in numpy + the C/OpenMP restatement of the
-    absent vpss search) on a bounded sample of the workload.  Returns
-    (Mpx/s, seconds, cores, sample description)."""
+def cpu_reference_run(threads):
+    """The reference's CPU implementation of the path -- the oracle port: the reference's own stages restated in numpy
+    (per-matrix LAPACK eigh spread over `threads` host threads) + the C/OpenMP restatement of the absent vpss search --
+    on a bounded sample of the workload.  Never imports vnlb_b200.  Returns (Mpx/s, seconds, description, psnr, outputs)."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)          # torchrun exports 1; the C search reads it at first use
     from oracle import vnlb_oracle as orc
     import torch
-    clean, noisy = make_video(1)
+    torch.set_num_threads(threads)
+    orc.set_num_threads(threads)
     s = CPU_SAMPLE
-    crop = np.ascontiguousarray(noisy[:s["T"], :, :s["H"], :s["W"]])
+    clean, flows = orc.synth_video(s["T"], WORK["H"], WORK["W"], 123, return_flows=True, crop=(s["H"], s["W"]))
+    noisy = orc.add_noise(clean, SIGMA, 123)
     torch.manual_seed(123)
     t0 = time.time()
-    orc.denoise(crop, SIGMA)
+    deno, basic, _ = orc.denoise(noisy, SIGMA, flows=flows)
     dt = time.time() - t0
     px = s["T"] * s["H"] * s["W"]
-    cores = max(orc.lib().oracle_num_threads(), torch.get_num_threads())
-    desc = "top-left %dx%dx%d crop of the workload, full vnlb.denoise (steps 1+2), default_params" % (
-        s["W"], s["H"], s["T"])
-    return px / 1e6 / dt, dt, cores, desc
+    desc = ("top-left %dx%dx%d crop of the workload (sigma=10, with its flows), full vnlb.denoise (steps 1+2), "
+            "default_params" % (s["W"], s["H"], s["T"]))
+    psnr = dict(basic=float(orc.compute_psnrs(basic, clean).mean()), deno=float(orc.compute_psnrs(deno, clean).mean()))
+    return px / 1e6 / dt, dt, desc, psnr, dict(clean=clean, noisy=noisy, flows=flows, deno=deno, basic=basic)
+
+
+def cpu_config1(threads):
+    """BASELINE configs[0]: davis_64x64-shaped synthetic RGB, 3 frames, sigma=20, vnlb.denoise on the CPU."""
+    from oracle import vnlb_oracle as orc
+    import torch
+    orc.set_num_threads(threads)
+    clean = orc.synth_video(3, 64, 64, 123)
+    noisy = orc.add_noise(clean, 20., 123)
+    torch.manual_seed(123)
+    t0 = time.time()
+    deno, basic, _ = orc.denoise(noisy, 20.)
+    dt = time.time() - t0
+    return dict(workload="64x64x3 synthetic RGB, sigma=20, no flow (BASELINE configs[0])", seconds=dt,
+                Mpx_per_s=3 * 64 * 64 / 1e6 / dt, cores=threads, kind="port",
+                psnr=dict(noisy=float(orc.compute_psnrs(noisy, clean).mean()), basic=float(orc.compute_psnrs(basic, clean).mean()),
+                          deno=float(orc.compute_psnrs(deno, clean).mean()))), (clean, noisy, deno, basic)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    threads = host_threads()
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, cores, desc = cpu_reference_run()
+        v, dt, desc, psnr, _ = cpu_reference_run(threads)
         if i >= args.warmup:
             vals.append((v, dt))
     v = float(np.mean([a for a, _ in vals]))
     ms = float(np.mean([b for _, b in vals])) * 1e3
     line = dict(metric=METRIC, value=v, unit="Mpx/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                ms_per_step=ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
-                config=dict(workload="854x480x20 synthetic RGB, sigma=20, no flow (BASELINE configs[1]); "
-                                     "each step = bounded sample: " + desc),
-                cpu_baseline=dict(value=v, unit="Mpx/s", cores=cores, kind="port", sample=desc),
-                e2e=dict(value=v, unit="Mpx/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                config=dict(workload=WORKLOAD_DESC + "; each step = bounded sample: " + desc),
+                cpu_baseline=dict(value=v, unit="Mpx/s", cores=threads, kind="port", sample=desc),
+                e2e=dict(value=v, unit="Mpx/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), psnr=psnr)
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import vnlb_b200
-    from vnlb_b200 import _lib, dist as vdist
+    from vnlb_b200 import _lib, dist as vdist, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -152,19 +189,26 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    clean, noisy = make_video(n_gpus)
-    T, C, H, W = noisy.shape
+    T, H, W = (args.frames or WORK["T"]), WORK["H"], WORK["W"]
     mpx = T * H * W / 1e6
-    noisy_pin = torch.from_numpy(noisy).pin_memory()
+    clean, flows_np = synth.synth_video(T, H, W, 123, return_flows=True)
+    noisy = synth.add_noise(clean, SIGMA, 123)
+    noisy_alt = synth.add_noise(clean, SIGMA_ALT, 123)
+    if rank != 0:
+        clean = None
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    noisy_pin = pin(noisy)
+    flows_pin = dict(fflow=pin(flows_np["fflow"]), bflow=pin(flows_np["bflow"]))
     noisy_dev = noisy_pin.to(device)
-    out_pin = torch.empty_like(noisy_pin).pin_memory()
-    params = vnlb_b200.get_params(SIGMA)
+    flows_dev = dict(fflow=flows_pin["fflow"].to(device), bflow=flows_pin["bflow"].to(device))
+    out_pin = torch.empty_like(noisy_pin).pin_memory() if rank == 0 else None
+    del flows_np
 
-    def call(x, stats=None):
+    def call(x, fl, sigma=SIGMA, stats=None, params=None):
+        params = params if params is not None else vnlb_b200.get_params(sigma)
         if world > 1:
-            return vdist.denoise_distributed(x, SIGMA, schedule="fast", params=params, stats=stats, device=device,
-                                             balance=BALANCE)
-        return vnlb_b200.denoise(x, SIGMA, gpuid=local_rank, verbose=False, schedule="fast", params=params, stats=stats)
+            return vdist.denoise_distributed(x, sigma, flows=fl, params=params, stats=stats, device=device, max_flow=MAX_FLOW)
+        return vnlb_b200.denoise(x, sigma, gpuid=local_rank, verbose=False, flows=fl, schedule="fast", params=params, stats=stats)
 
     def barrier():
         if world > 1:
@@ -178,51 +222,46 @@ def run_ours(args):
         gc.collect()
         gc.disable()        # a full collection of the interpreter heap (~100 ms) inside a step is a host stall, not GPU time
         try:
-            return _timed(fn, steps, tag)
+            barrier()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            evs[0].record()
+            for i in range(steps):
+                fn()
+                evs[i + 1].record()
+            barrier()
+            per_step[tag] = [round(evs[i].elapsed_time(evs[i + 1]), 1) for i in range(steps)]
+            ms = torch.tensor([evs[0].elapsed_time(evs[steps])], device=device)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
         finally:
             gc.enable()
 
-    def _timed(fn, steps, tag):
-        barrier()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        evs[0].record()
-        for i in range(steps):
-            fn()
-            evs[i + 1].record()
-        barrier()
-        per_step[tag] = [round(evs[i].elapsed_time(evs[i + 1]), 1) for i in range(steps)]
-        ms = torch.tensor([evs[0].elapsed_time(evs[steps])], device=device)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    # the clock sampler starts before the warm-up so that spawning nvidia-smi never lands in a timed region;
-    # only the samples taken during the timed regions are reported
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-
     result = {}
 
     def step_dev():
-        result["deno"], result["basic"], _ = call(noisy_dev)
+        result["deno"], result["basic"], _ = call(noisy_dev, flows_dev)
 
-    # ---- warm-up: the same step as the timed one, so kernels are loaded and the caching allocator has
-    #      reached its steady state (a first-time cudaMalloc inside a step costs 50-100 ms) ----
+    # ---- warm-up: the same step as the timed one (kernels loaded, caching allocator in its steady state) ----
     for _ in range(args.warmup):
         step_dev()
 
     # ---- device-resident throughput (`value`) ----
     l0 = int(_lib.lib.vnlb_kernel_launches())   # kernels launched by libvnlb_b200.so, counted in the library
-
-    if rank == 0:   # sample the clocks every 64th kernel launch of the timed steps: the GPU is busy at those moments
+    if rank == 0:   # sample the clocks every 64th C-ABI call of the timed steps: the GPU is busy at those moments
         _lib.on_launch = lambda n: sampler.sample() if n % 64 == 0 else None
     ms = timed(step_dev, args.steps, "value")
     launches = (int(_lib.lib.vnlb_kernel_launches()) - l0) // max(args.steps, 1)
 
-    # ---- end to end through the public API with host buffers (`e2e`) ----
+    # ---- end to end through the public API with HOST buffers (`e2e`): video + flows host->device (each rank only its
+    #      band + halo rows), result device->host on rank 0, all inside the timed region ----
+    st_e2e = {}
+
     def step_e2e():
-        d, _, _ = call(noisy_pin)
+        d, _, _ = call(noisy_pin, flows_pin, stats=st_e2e)
         if rank == 0:
             out_pin.copy_(d, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -232,11 +271,24 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps, "e2e")
     _lib.on_launch = None
     clocks = sampler.summary() if rank == 0 else None
+    rows_copied = st_e2e.get("layout", {}).get("rows_copied", H)
+    h2d = torch.tensor([float(rows_copied) * W * T * (3 + 4) * 4], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(h2d)
+    h2d_bytes = int(h2d.item())
 
-    # ---- per-stage device time -> roofline of the dominant kernel (rank 0 timing, max over ranks skipped) ----
+    # ---- the other noise level of configs[4] ----
+    noisy_alt_dev = torch.from_numpy(noisy_alt).to(device)
+    call(noisy_alt_dev, flows_dev, SIGMA_ALT)
+    st_alt = {}
+    n_alt = max(1, min(args.steps, 3))
+    ms_alt = timed(lambda: result.__setitem__("alt", call(noisy_alt_dev, flows_dev, SIGMA_ALT, st_alt)), n_alt, "sigma50")
+    deno_alt = result.pop("alt")[0]
+
+    # ---- per-stage device time (CUDA events on the launching streams) -> roofline of the dominant stage ----
     _lib.timer = _lib.StageTimer()
     st2 = {}
-    call(noisy_dev, st2)
+    call(noisy_dev, flows_dev, stats=st2)
     stage = _lib.timer.summary()
     _lib.timer = None
     ngroups = [int(g) for g in st2.get("ngroups", [0, 0])]
@@ -250,16 +302,22 @@ def run_ours(args):
         dist.all_gather(all_steps, mine_steps)
         per_rank = dict(groups=[int(a[0].item()) for a in allr], stage_ms=[round(float(a[1].item()), 1) for a in allr],
                         value_step_ms=[[round(float(x), 1) for x in a.tolist()] for a in all_steps],
-                        allreduce_ms_rank0=[round(x, 2) for x in st2.get("allreduce_ms", [])])
+                        exchange_ms_rank0=[round(x, 2) for x in st2.get("exchange_ms", [])],
+                        exchange_bytes_rank0=st2.get("exchange_bytes"), layout_rank0=st2.get("layout"))
 
     if rank == 0:
-        hbm_peak, peak_kind = load_peaks()
-        deno = result["deno"].cpu().numpy()
-        basic = result["basic"].cpu().numpy()
-        psnr = dict(noisy=float(vnlb_b200.compute_psnrs(noisy, clean).mean()),
-                    basic=float(vnlb_b200.compute_psnrs(basic, clean).mean()),
-                    deno=float(vnlb_b200.compute_psnrs(deno, clean).mean()))
-        # stage keys are "<stage>_s<step>"; merge per stage for the summary
+        hbm_peak, hbm_kind, fp32_peak, fp32_kind, fp32_rec = load_peaks()
+        psnr_of = lambda x, ref=clean: float(vnlb_b200.compute_psnrs(x.cpu().numpy() if torch.is_tensor(x) else x, ref).mean())
+        psnr = dict(noisy=psnr_of(noisy), basic=psnr_of(result["basic"]), deno=psnr_of(result["deno"]))
+        psnr_alt = dict(noisy=psnr_of(noisy_alt), deno=psnr_of(deno_alt))
+        psnr_delta = {}
+        if world > 1:
+            # the same video on ONE GPU (outside the timed region): multi-GPU output within the PSNR tolerance of it
+            d1, b1, _ = vnlb_b200.denoise(noisy_dev, SIGMA, gpuid=local_rank, verbose=False, flows=flows_dev, schedule="fast")
+            psnr_delta["vs_n1_deno_db"] = psnr["deno"] - psnr_of(d1)
+            psnr_delta["vs_n1_basic_db"] = psnr["basic"] - psnr_of(b1)
+            del d1, b1
+        # stage keys are "<stage>_s<step>"
         merged = {}
         for k, v in stage.items():
             base = k.rsplit("_s", 1)[0]
@@ -267,66 +325,150 @@ def run_ours(args):
             m["ms"] += v["ms"]
             m["launches"] += v["launches"]
         step_ms = sum(v["ms"] for v in merged.values())
-        dom = max(merged, key=lambda k: merged[k]["ms"]) if merged else None
-        # algorithmic work per group (SURVEY 8d / DESIGN.md section 5), per VNLB step: k = 100 / 60, p = 98, C = 3
-        #   fused Bayes: gather k*D*4 (noisy; + basic in step 2) + scatter k*(D+p)*4 ; nominal flop count 35.8 / 31.7 MFLOP
-        #   search: N_cand*p*C_d*3 flops, (k*12 + 24) bytes
-        work = {
-            "bayes": [dict(bytes=100 * 294 * 4 + 100 * 392 * 4, flops=35.8e6),
-                      dict(bytes=2 * 60 * 294 * 4 + 60 * 392 * 4, flops=31.7e6)],
-            "search": [dict(bytes=100 * 12 + 24, flops=9477 * 98 * 1 * 3), dict(bytes=60 * 12 + 24, flops=9477 * 98 * 3 * 3)],
-            "mask_fill_flat": [dict(bytes=100 * 294 * 4, flops=0.), dict(bytes=2 * 60 * 294 * 4, flops=0.)],
-            "aggregate": [dict(bytes=100 * 294 * 4, flops=100 * 392.), dict(bytes=60 * 294 * 4, flops=60 * 392.)],
-        }
-        # DRAM bytes per group of the fused Bayes stage from the ncu --set full capture (profiles/r1b_summary.md, all kernels
-        # of a call summed: the per-problem workspace the split kernels hand over is what reaches DRAM; the gathers hit L2)
-        ncu_dram_bytes_per_group = {"bayes": [260e3, 104e3]}
+        # Algorithmic work per group (SURVEY 8d / DESIGN.md section 5), per VNLB step: k = 100 / 60, p = 98, C = 3.
+        #   fused Bayes: nominal LAPACK-style flop count 35.8 / 31.7 MFLOP; bytes = gather k*D*4 (noisy; + basic in step 2)
+        #   + scatter k*(D+p)*4.  search: N_cand*p*C_d*3 flops.
+        bayes_flops, bayes_bytes = [35.8e6, 31.7e6], [100 * 294 * 4 + 100 * 392 * 4, 2 * 60 * 294 * 4 + 60 * 392 * 4]
+        traffic_rec = load_ncu_traffic()
         roof = None
+        dom = "bayes_s0" if "bayes_s0" in stage else None
         if dom:
-            d = merged[dom]
-            alg_bytes = sum(work[dom][s]["bytes"] * ngroups[s] for s in (0, 1))
-            alg_flops = sum(work[dom][s]["flops"] * ngroups[s] for s in (0, 1))
+            d = stage[dom]
             sec = d["ms"] / 1e3
+            flops = bayes_flops[0] * ngroups[0]
+            byts = bayes_bytes[0] * ngroups[0]
+            per_launch_groups = ngroups[0] / max(d["launches"], 1)
             traffic = None
-            if dom in ncu_dram_bytes_per_group:
-                traffic = sum(ncu_dram_bytes_per_group[dom][s] * ngroups[s] for s in (0, 1)) / max(d["launches"], 1)
-            roof = dict(kernel="vnlb_bayes_aggregate_fused: cov_tridiag_kernel + tridiag_tail_kernel + bayes_kernel<fused,split> "
-                               "(step 1), gram_tridiag_kernel + tridiag_tail_kernel + bayes_kernel<fused,gram,split> (step 2)" if dom == "bayes" else dom, bound="hbm",
-                        achieved=alg_bytes / sec / 1e9, peak=hbm_peak, unit="GB/s",
-                        frac=alg_bytes / sec / 1e9 / hbm_peak, traffic=traffic, peak_kind=peak_kind,
-                        algorithmic_bytes_per_launch=alg_bytes / max(d["launches"], 1),
-                        launches=d["launches"], avg_launch_ms=d["ms"] / max(d["launches"], 1),
-                        launch_unit="one C-ABI call of the fused Bayes stage = one round of groups (4 kernels in step 1, 3 in step 2)",
-                        share_of_step=d["ms"] / max(step_ms, 1e-9),
-                        note="not an HBM-bound stage (arithmetic intensity ~130 flop/B, ridge ~11; ncu: DRAM 1-7 % of peak): its kernels "
-                             "are bound by the shared-memory data pipe (58-77 % busy) and dependent chains; the HBM fraction is small "
-                             "by construction, see fp32 and profiles/r1b_summary.md",
-                        fp32=dict(achieved_tflops=alg_flops / sec / 1e12, nominal_peak_tflops=74.4,
-                                  frac=alg_flops / sec / 1e12 / 74.4,
-                                  note="nominal LAPACK-style flop count of SURVEY 8d over nominal 148 SM x 128 lanes x 2 x 1.965 GHz"))
-        stage = {k: v for k, v in sorted(stage.items())}
+            if traffic_rec and "bayes_step1_dram_bytes_per_group" in traffic_rec:
+                traffic = traffic_rec["bayes_step1_dram_bytes_per_group"] * per_launch_groups
+            roof = dict(
+                kernel="vnlb_bayes_aggregate_fused, VNLB step 1 (cov_tridiag_kernel + 2 x tridiag_tail_kernel + bayes_kernel<fused,split>): "
+                       "gather + covariance + eigen-decomposition + Wiener filter + aggregation of one round of groups",
+                bound="fp32", achieved=flops / sec / 1e12, peak=fp32_peak, unit="TFLOP/s", frac=flops / sec / 1e12 / fp32_peak,
+                peak_kind=fp32_kind, traffic=traffic,
+                traffic_source=(traffic_rec or {}).get("source", None),
+                algorithmic_flops_per_launch=bayes_flops[0] * per_launch_groups,
+                algorithmic_bytes_per_launch=bayes_bytes[0] * per_launch_groups,
+                launches=d["launches"], avg_launch_ms=d["ms"] / max(d["launches"], 1),
+                launch_unit="one C-ABI call = one round of groups (4 kernels)", share_of_step=d["ms"] / max(step_ms, 1e-9),
+                flop_count="nominal LAPACK-style count of SURVEY 8d (cov 2kp^2C + eig 9p^3C + filter 4kprC = 35.8 MFLOP per group); "
+                           "the kernels execute fewer: only the eigenpairs above the Wiener threshold are computed",
+                ncu=(traffic_rec or {}).get("bayes_step1_pipes", None),
+                hbm=dict(achieved=byts / sec / 1e9, peak=hbm_peak, unit="GB/s", frac=byts / sec / 1e9 / hbm_peak, peak_kind=hbm_kind,
+                         note="not the binding roof: arithmetic intensity ~130 flop/B against a ridge of ~10"),
+                step2=dict(achieved=bayes_flops[1] * ngroups[1] / (stage["bayes_s1"]["ms"] / 1e3) / 1e12,
+                           frac=bayes_flops[1] * ngroups[1] / (stage["bayes_s1"]["ms"] / 1e3) / 1e12 / fp32_peak,
+                           note="nominal count of the p x p problem; the kernel solves the 60 x 60 Gram problem (SURVEY: ~12 MFLOP)")
+                if "bayes_s1" in stage else None)
+        srch = {}
+        for s_ in (0, 1):
+            key = "search_s%d" % s_
+            if key in stage and ngroups[s_]:
+                dc = 1 if s_ == 0 else 3
+                q = ngroups[s_] + (st2.get("ndropped", [0, 0])[s_] if st2.get("ndropped") else 0)
+                tf = 9477 * 98 * dc * 3 * q / (stage[key]["ms"] / 1e3) / 1e12
+                srch["step%d" % (s_ + 1)] = dict(queries=q, ms=stage[key]["ms"], Mqueries_per_s=q / stage[key]["ms"] / 1e3,
+                                                 algorithmic_tflops=tf, frac_of_fp32_peak=tf / fp32_peak)
+        extras = {}
         cpu = None
-        if n_gpus == 1 and not args.no_cpu_baseline:
-            v, dt, cores, desc = cpu_reference_run()
-            cpu = dict(value=v, unit="Mpx/s", cores=cores, kind="port", sample=desc, seconds=dt)
+        if n_gpus == 1 and not args.quick:
+            extras, cpu = single_gpu_extras(vnlb_b200, device, fp32_peak, hbm_peak, psnr_delta, args)
         line = dict(
             metric=METRIC, value=mpx * args.steps / (ms / 1e3), unit="Mpx/s", n_gpus=n_gpus, steps=args.steps,
-            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+            warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong",
             vs_baseline=None, dtype="f32", data="synthetic",
-            config=dict(workload="%dx%dx%d synthetic RGB, sigma=20, no flow (BASELINE configs[1]%s)" % (
-                W, H, T, "" if n_gpus == 1 else ", %d bands of 480 rows, one per GPU" % n_gpus),
-                params="default_params: 7x7x2 patches, 27x27 window, +-6 frames, k=100/60, rank 39",
-                schedule="fast", l2="working set (noisy+basic+accumulators %.0f MB) exceeds the 126 MB L2" % (
-                    T * H * W * 4 * 10 / 1e6)),
+            config=dict(workload=WORKLOAD_DESC if T == WORK["T"] else WORKLOAD_DESC + " [frames overridden: %d]" % T,
+                        params="default_params: 7x7x2 patches, 27x27 window, +-6 frames, k=100/60, rank 39",
+                        schedule="fast (device-side rounds, in-round conflict resolution)",
+                        parallelism="1 GPU" if n_gpus == 1 else "%d row bands + halo, border-strip exchange (NCCL send/recv)" % n_gpus,
+                        l2="working set (noisy + flows + basic + accumulators ~%.1f GB) exceeds the 126 MB L2" % (T * H * W * 4 * 14 / 1e9)),
             e2e=dict(value=mpx * args.steps / (ms_e2e / 1e3), unit="Mpx/s", ms_per_step=ms_e2e / args.steps,
-                     h2d_bytes_per_step=int(noisy.nbytes) * max(world, 1), d2h_bytes_per_step=int(noisy.nbytes)),
-            gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
-            stages_ms={k: round(v["ms"], 3) for k, v in stage.items()}, groups_per_step=ngroups, psnr=psnr,
-            rounds=st2.get("nrounds"), per_rank=per_rank, per_step_ms_rank0=per_step)
+                     h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=int(noisy.nbytes),
+                     note="video + forward/backward flows host->device (each rank its band + halo rows only), estimate device->host on rank 0"),
+            sigma50=dict(value=mpx * n_alt / (ms_alt / 1e3), unit="Mpx/s", ms_per_step=ms_alt / n_alt, steps=n_alt,
+                         groups_per_step=[int(g) for g in st_alt.get("ngroups", [])][-2:], psnr=psnr_alt),
+            gpu_launches=int(launches), clocks=clocks, roofline=roof, search=srch, cpu_baseline=cpu,
+            stages_ms={k: round(v["ms"], 3) for k, v in sorted(stage.items())}, groups_per_step=ngroups,
+            dropped_per_step=st2.get("ndropped"), psnr=psnr, psnr_delta=psnr_delta or None,
+            rounds=st2.get("nrounds"), per_rank=per_rank, per_step_ms_rank0=per_step, **extras)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def single_gpu_extras(vnlb_b200, device, fp32_peak, hbm_peak, psnr_delta, args):
+    """N = 1 only, outside the timed regions: the remaining BASELINE configurations and the parity evidence of the benched
+    schedule.  Returns (extra keys of the JSON line, cpu_baseline)."""
+    import torch
+    from vnlb_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import microbench
+    dev = str(device)
+    psnr_of = lambda x, ref: float(vnlb_b200.compute_psnrs(x.cpu().numpy() if torch.is_tensor(x) else x, ref).mean())
+    extras = {}
+    torch.cuda.empty_cache()
+    # ---- BASELINE configs[1]: 854x480x20, sigma=20, no flow ----
+    c2 = CFG2
+    clean2 = synth.synth_video(c2["T"], c2["H"], c2["W"], 123)
+    noisy2 = torch.from_numpy(synth.add_noise(clean2, c2["sigma"], 123)).to(device)
+    for _ in range(2):
+        vnlb_b200.denoise(noisy2, c2["sigma"], gpuid=device.index, verbose=False)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    n2 = 3
+    torch.cuda.synchronize()
+    evs[0].record()
+    for _ in range(n2):
+        st = {}
+        d2, b2, _ = vnlb_b200.denoise(noisy2, c2["sigma"], gpuid=device.index, verbose=False, stats=st)
+    evs[1].record()
+    torch.cuda.synchronize()
+    ms2 = evs[0].elapsed_time(evs[1]) / n2
+    extras["config2"] = dict(workload="854x480x20 synthetic RGB, sigma=20, no flow (BASELINE configs[1])",
+                             value=c2["T"] * c2["H"] * c2["W"] / 1e6 / (ms2 / 1e3), unit="Mpx/s", ms_per_step=ms2, steps=n2,
+                             groups_per_step=st["ngroups"], dropped_per_step=st.get("ndropped"),
+                             psnr=dict(basic=psnr_of(b2, clean2), deno=psnr_of(d2, clean2)))
+    del noisy2, d2, b2
+    # ---- benched schedule vs the reference-exact schedule on a sub-video of the workload (sigma=10, with flows) ----
+    s = PARITY_SUB
+    cs, fs = synth.synth_video(s["T"], WORK["H"], WORK["W"], 123, return_flows=True, crop=(s["H"], s["W"]))
+    ns = synth.add_noise(cs, SIGMA, 123)
+    torch.manual_seed(123)
+    sp, sf = {}, {}
+    dp, bp, _ = vnlb_b200.denoise(ns, SIGMA, gpuid=device.index, verbose=False, flows=fs, schedule="parity", stats=sp)
+    df, bf, _ = vnlb_b200.denoise(ns, SIGMA, gpuid=device.index, verbose=False, flows=fs, schedule="fast", stats=sf)
+    psnr_delta["fast_vs_parity_schedule"] = dict(
+        video="top-left %dx%dx%d crop of the workload" % (s["W"], s["H"], s["T"]),
+        deno_db=psnr_of(df, cs) - psnr_of(dp, cs), basic_db=psnr_of(bf, cs) - psnr_of(bp, cs),
+        groups_parity=sp["ngroups"], groups_fast=sf["ngroups"], dropped_fast=sf.get("ndropped"))
+    del dp, bp, df, bf
+    # ---- CPU baseline (oracle port, all host cores) on a bounded sample + the benched schedule on the same sample ----
+    threads = host_threads()
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, dt, desc, opsnr, o = cpu_reference_run(threads)
+        cpu = dict(value=v, unit="Mpx/s", cores=threads, kind="port", sample=desc, seconds=dt, psnr=opsnr)
+        dg, bg, _ = vnlb_b200.denoise(o["noisy"], SIGMA, gpuid=device.index, verbose=False, flows=o["flows"], schedule="fast")
+        torch.manual_seed(123)
+        dq, bq, _ = vnlb_b200.denoise(o["noisy"], SIGMA, gpuid=device.index, verbose=False, flows=o["flows"], schedule="parity")
+        psnr_delta["vs_cpu_oracle_on_cpu_sample"] = dict(
+            fast_deno_db=psnr_of(dg, o["clean"]) - opsnr["deno"], fast_basic_db=psnr_of(bg, o["clean"]) - opsnr["basic"],
+            parity_deno_db=psnr_of(dq, o["clean"]) - opsnr["deno"], parity_basic_db=psnr_of(bq, o["clean"]) - opsnr["basic"],
+            parity_max_abs_deno=float(np.abs(dq.cpu().numpy() - o["deno"]).max()),
+            parity_max_abs_basic=float(np.abs(bq.cpu().numpy() - o["basic"]).max()))
+        # ---- BASELINE configs[0]: 64x64x3 on the CPU, and the CUDA path on the same input ----
+        c1, (cl1, no1, od1, ob1) = cpu_config1(threads)
+        torch.manual_seed(123)
+        d1, b1, _ = vnlb_b200.denoise(no1, 20., gpuid=device.index, verbose=False, schedule="parity")
+        c1["gpu_parity_schedule_max_abs"] = dict(deno=float(np.abs(d1.cpu().numpy() - od1).max()),
+                                                 basic=float(np.abs(b1.cpu().numpy() - ob1).max()))
+        extras["config1_cpu"] = c1
+    # ---- BASELINE configs[2] / configs[3]: microbenchmarks on the shipped kernels ----
+    torch.cuda.empty_cache()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    extras["config3_search"] = microbench.search_microbench(dev, 65536, fp32_peak, flush)
+    extras["config4_bayes"] = microbench.bayes_microbench(dev, 16384, fp32_peak, hbm_peak, flush)
+    return extras, cpu
 
 
 def main():
@@ -336,10 +478,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the N = 1 extras (other BASELINE configs, parity evidence, CPU baseline)")
     ap.add_argument("--frames", type=int, default=None, help="override frame count (debugging only)")
     args = ap.parse_args()
-    if args.frames:
-        BASE["T"] = args.frames
     if args.impl == "reference":
         run_reference(args)
     else:

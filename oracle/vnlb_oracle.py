@@ -282,6 +282,36 @@ def exec_flat_areas(pnoisy, gamma, sigma2):
 # Bayes estimate  (lib/vnlb/deno/bayes_est.py)
 # ----------------------------------------------------------------------------
 
+_EIGH_THREADS = 1
+
+
+def set_num_threads(n):
+    """Host threads of the batched eigendecomposition (the dominant CPU cost; bench.py's CPU arm sets it to the core
+    count -- numpy's batched eigh is a serial loop over LAPACK calls that releases the GIL, so the batch is split
+    over a thread pool; per-matrix results are unchanged).  The C search uses OpenMP (OMP_NUM_THREADS)."""
+    global _EIGH_THREADS
+    _EIGH_THREADS = max(1, int(n))
+
+
+def _eigh_batched(cov):
+    """np.linalg.eigh over the batch.  98 x 98 problems are far below the size where a threaded BLAS pays: OpenBLAS'
+    own threads are limited to 1 inside (measured here: 10.2 s -> 4.3 s for 3072 matrices) and the batch is split
+    over `_EIGH_THREADS` host threads instead (-> 1.6 s on 8 vCPUs)."""
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:                                   # pragma: no cover
+        from contextlib import nullcontext as threadpool_limits
+    nt = min(_EIGH_THREADS, cov.shape[0] // 8)
+    with threadpool_limits(limits=1):
+        if nt <= 1:
+            return np.linalg.eigh(cov)
+        from concurrent.futures import ThreadPoolExecutor
+        chunks = np.array_split(np.arange(cov.shape[0]), nt)
+        with ThreadPoolExecutor(nt) as ex:
+            parts = list(ex.map(lambda ix: np.linalg.eigh(cov[ix[0]:ix[-1] + 1]), chunks))
+    return np.concatenate([p[0] for p in parts], 0), np.concatenate([p[1] for p in parts], 0)
+
+
 def bayes_denoise(pnoisy, pbasic, flat, args, return_parts=False):
     """bayes_est.denoise, lib/vnlb/deno/bayes_est.py:17-62.
 
@@ -308,7 +338,7 @@ def bayes_denoise(pnoisy, pbasic, flat, args, return_parts=False):
     Bf = B.reshape(b * c, n, -1)
     pin = Xf if args.cpatches == "noisy" else Bf
     cov = np.matmul(pin.transpose(0, 2, 1), pin) / np.float32(n)
-    evals, evecs = np.linalg.eigh(cov)
+    evals, evecs = _eigh_batched(cov)
     evals = evals[:, ::-1].astype(np.float32).copy()
     evecs = evecs[:, :, ::-1][:, :, :args.rank].astype(np.float32)
     rank_var = evals.reshape(b, c, -1).sum(2).mean(1)            # :39-40
@@ -456,16 +486,19 @@ def compute_psnrs(deno, clean, imax=255.):
 # synthetic data: shared by tests and bench
 # ----------------------------------------------------------------------------
 
-def synth_video(T, H, W, seed=123, C=3, return_flows=False):
+def synth_video(T, H, W, seed=123, C=3, return_flows=False, crop=None):
     """Deterministic clean video: smooth field + textured rectangles that
     translate 1-2 px/frame; range 0..255, float32 [T,C,H,W].  Also returns the
     analytic forward/backward flows [T,2,H,W] (ch0 = dx, ch1 = dy) of the
     background (zero) -- per-object motion is small and only approximate."""
     rng = np.random.RandomState(seed)
-    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
-    vid = np.zeros((T, C, H, W), np.float32)
-    ff = np.zeros((T, 2, H, W), np.float32) if return_flows else None
-    bf = np.zeros((T, 2, H, W), np.float32) if return_flows else None
+    # crop = (Hc, Wc): only the top-left Hc x Wc corner of the H x W video is materialised (same content as cropping
+    # the full video; the CPU baseline's bounded sample of a 1080p workload)
+    Hc, Wc = (H, W) if crop is None else (min(int(crop[0]), H), min(int(crop[1]), W))
+    yy, xx = np.meshgrid(np.arange(Hc, dtype=np.float32), np.arange(Wc, dtype=np.float32), indexing="ij")
+    vid = np.zeros((T, C, Hc, Wc), np.float32)
+    ff = np.zeros((T, 2, Hc, Wc), np.float32) if return_flows else None
+    bf = np.zeros((T, 2, Hc, Wc), np.float32) if return_flows else None
     nrect = 6
     rects = []
     for _ in range(nrect):
@@ -482,7 +515,7 @@ def synth_video(T, H, W, seed=123, C=3, return_flows=False):
         for (y0, x0, rh, rw, vy, vx, tex) in rects:
             ya, xa = y0 + vy * t, x0 + vx * t
             ys, xs = max(0, ya), max(0, xa)
-            ye, xe = min(H, ya + rh), min(W, xa + rw)
+            ye, xe = min(Hc, ya + rh), min(Wc, xa + rw)
             if ye > ys and xe > xs:
                 vid[t, :, ys:ye, xs:xe] = tex[:, ys - ya:ye - ya, xs - xa:xe - xa]
                 if return_flows:     # the object's own translation (the last-drawn object wins, as in the frame)

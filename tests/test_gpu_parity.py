@@ -275,14 +275,16 @@ def test_aggregate(vb, golden_dir):
 
 
 # ---------------------------------------------------------------- end to end
-def test_e2e_parity_schedule_vs_golden_and_oracle(vb, golden_dir):
-    """vnlb_b200.denoise(schedule='parity') on the reference's seeded run:
-    max-abs 1e-2 and PSNR within 0.02 dB (north-star tolerance)."""
-    g = np.load(os.path.join(golden_dir, "e2e.npz"))
-    e = gin.E2E
+@pytest.mark.parametrize("case", ["e2e", "e2e_s10", "e2e_s50", "e2e_cfg1"])
+def test_e2e_parity_schedule_vs_golden_and_oracle(vb, golden_dir, case):
+    """vnlb_b200.denoise(schedule='parity') on the reference's seeded runs (sigma 20; sigma 10 / 50 = the noise levels
+    of BASELINE configs[4]; 3 x 64 x 64 = BASELINE configs[0]): max-abs 1e-2 and PSNR within 0.02 dB (north-star
+    tolerance), same processed-pixel sequence as the oracle."""
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    e = gin.E2E_CASES[case]
     clean = orc.synth_video(e["T"], e["H"], e["W"], e["seed"])
     noisy = orc.add_noise(clean, e["sigma"], e["seed"])
-    for eig in ("jacobi", "tridiag"):
+    for eig in (("jacobi", "tridiag") if case == "e2e" else ("tridiag",)):
         params = vb.get_params(e["sigma"])
         params["eig_method"] = [eig, eig]
         torch.manual_seed(e["torch_seed"])
@@ -300,21 +302,6 @@ def test_e2e_parity_schedule_vs_golden_and_oracle(vb, golden_dir):
         assert dt > 0
 
 
-# ---------------------------------------------------------------- Bayes: stress and odd shapes
-def _stress_stack(rs, n, ps, pt, scale, sigma=20., c=3, b=4):
-    p = pt * ps * ps
-    s2 = sigma * sigma
-    out = np.zeros((b, c, n, p), np.float32)
-    for g in range(b):
-        for ch in range(c):
-            basis = np.linalg.qr(rs.randn(p, 3))[0]
-            coef = rs.randn(n, 3) * np.sqrt(s2 * scale) * np.array([1., .5, .25])
-            out[g, ch] = coef @ basis.T + rs.randn(n, p) * sigma + rs.rand(1, p) * 100
-    return np.ascontiguousarray(out.reshape(b, c, n, pt, ps, ps).transpose(0, 2, 3, 1, 4, 5)).astype(np.float32)
-
-
-@pytest.mark.parametrize("scale,thresh,step", [(600., 2.7, 0), (600., 1.5, 0), (5000., 2.7, 0), (600., 0.7, 1),
-                                               (50., 0.3, 1), (0.0, 0.3, 1)])
 def test_bayes_tridiag_clustered_eigenvalues(vb, scale, thresh, step):
     """Many (up to rank = 39) tightly clustered noise eigenvalues above the threshold."""
     from vnlb_b200 import deno
@@ -528,7 +515,8 @@ def test_bayes_large_call_is_chunked_consistently(vb):
 
 
 def test_e2e_fast_schedule_psnr(vb, golden_dir):
-    """The throughput schedule (fused and staged) stays within the PSNR band of the parity run."""
+    """The throughput schedule (fused and staged) on the tiny golden clip: a coarse sanity band only (a 4x40x48 clip holds
+    ~300 groups; the 0.02 dB comparison is test_fast_schedule_vs_parity_schedule_320x240x8)."""
     g = np.load(os.path.join(golden_dir, "e2e.npz"))
     e = gin.E2E
     clean = orc.synth_video(e["T"], e["H"], e["W"], e["seed"])
@@ -539,6 +527,29 @@ def test_e2e_fast_schedule_psnr(vb, golden_dir):
         deno, basic, _ = vb.denoise(noisy, e["sigma"], schedule="fast", verbose=False, params=params)
         ps = [orc.compute_psnrs(a.cpu().numpy(), clean).mean() for a in (basic, deno)]
         assert abs(ps[0] - g["psnrs"][1]) < 0.25 and abs(ps[1] - g["psnrs"][2]) < 0.25, (fused, ps, g["psnrs"])
+
+
+@pytest.mark.parametrize("sigma", [10., 20., 50.])
+def test_fast_schedule_vs_parity_schedule_320x240x8(vb, sigma):
+    """The BENCHED schedule against the reference-exact one at a size where 0.02 dB means something (7-9 k groups per
+    step): final and basic PSNR within the north star's 0.02 dB, and no more groups than the reference schedule
+    processes + 3 % (the in-round conflict resolution removes the round-1 schedule's +30 % at this size)."""
+    from vnlb_b200 import synth
+    T, H, W = 8, 240, 320
+    clean, flows = synth.synth_video(T, H, W, 123, return_flows=True)
+    noisy = synth.add_noise(clean, sigma, 123)
+    torch.manual_seed(123)
+    sp, sf = {}, {}
+    dp, bp, _ = vb.denoise(noisy, sigma, schedule="parity", verbose=False, stats=sp, flows=flows)
+    df, bf, _ = vb.denoise(noisy, sigma, schedule="fast", verbose=False, stats=sf, flows=flows)
+    ps = lambda x: float(orc.compute_psnrs(x.cpu().numpy(), clean).mean())
+    res = dict(parity=(ps(bp), ps(dp)), fast=(ps(bf), ps(df)), groups_parity=sp["ngroups"], groups_fast=sf["ngroups"],
+               dropped=sf.get("ndropped"))
+    print(sigma, res)
+    assert abs(res["fast"][1] - res["parity"][1]) <= 0.02, res        # final estimate
+    assert abs(res["fast"][0] - res["parity"][0]) <= 0.02, res        # basic estimate
+    for s_ in (0, 1):
+        assert sf["ngroups"][s_] <= 1.03 * sp["ngroups"][s_], res
 
 
 # ---------------------------------------------------------------- end to end: flows and other parameter tables
@@ -670,6 +681,130 @@ def test_full_size_properties_854x480x20(vb):
     ref = yuv[:, 0][wts > 0]
     assert float((est - ref).abs().mean()) < 0.8 * sigma * 3 ** 0.5            # estimate is closer than the noise (Y has std sigma)
     assert torch.isfinite(images.deno).all()
+
+
+def test_search_bit_exact_256_queries_960x540_config3(vb):
+    """BASELINE configs[2] (search microbench: 7x7x2 patches, 27x27 window, +-4 frames, k = 100 at 960x540): 256
+    queries spread over the lattice, indices AND distances bit-identical to the CPU oracle, steps 1 (luminance
+    distance) and 2 (all channels), with and without flows."""
+    from vnlb_b200 import color, mask as gm, search, synth
+    T, H, W, sigma = 16, 540, 960, 20.
+    clean, flows = synth.synth_video(T, H, W, 123, return_flows=True)
+    yuv = color.rgb2yuv(cu(synth.add_noise(clean, sigma)))
+    yuv_np = yuv.cpu().numpy()
+    dflows = SimpleNamespace(fflow=cu(flows["fflow"]), bflow=cu(flows["bflow"]))
+    for step in (0, 1):
+        a = gargs(vb, step, sizeSearchTimeFwd=4, sizeSearchTimeBwd=4, nSimilarPatches=100)
+        oa = oargs(step, sizeSearchTimeFwd=4, sizeSearchTimeBwd=4, nSimilarPatches=100)
+        m, nset = gm.init_mask(yuv.shape, a, DEV)
+        q = torch.nonzero(m)[:: nset // 256][:256].contiguous()
+        for fl, ofl in ((None, None), (dflows, flows)):
+            vals = torch.empty((256, 100), device=DEV)
+            inds = torch.empty((256, 100), dtype=torch.int64, device=DEV)
+            search.exec_sim_search_burst(yuv, q, vals, inds, fl, sigma, a)
+            ov = np.full((256, 100), np.inf, np.float32)
+            oi = np.full((256, 100), -1, np.int64)
+            orc.exec_sim_search_burst(yuv_np, q.cpu().numpy(), ov, oi, ofl, sigma, oa)
+            assert np.array_equal(oi, inds.cpu().numpy()), (step, fl is not None)
+            assert np.array_equal(ov, vals.cpu().numpy()), (step, fl is not None)
+
+
+@pytest.mark.parametrize("window_mode", ["shift", "clip"])
+def test_search_vs_independent_torch_bruteforce(vb, window_mode):
+    """The search against an INDEPENDENT brute force written with torch ops in float64 (no code shared with the oracle
+    or the kernels; ADVICE r1: the oracle-vs-kernel tests are two restatements by one author): same neighbour sets
+    up to float32-level ties, same distances to 1e-5 relative, for both window modes (the semantic that is an
+    assumption about the absent vpss)."""
+    from vnlb_b200 import search
+    T, C, H, W, ps, pt, ws_, nwt, k = 5, 3, 40, 44, 7, 2, 27, 2, 60
+    rs = np.random.RandomState(5)
+    img = (rs.rand(T, C, H, W) * 255).astype(np.float32)
+    a = gargs(vb, 1, sizeSearchTimeFwd=nwt, sizeSearchTimeBwd=nwt, nSimilarPatches=k, window_mode=window_mode)
+    qs = np.array([[0, 0, 0], [2, 17, 20], [3, 33, 37], [1, 5, 30], [3, 20, 0]], np.int64)
+    vals = torch.empty((len(qs), k), device=DEV)
+    inds = torch.empty((len(qs), k), dtype=torch.int64, device=DEV)
+    search.exec_sim_search_burst(cu(img), cu(qs), vals, inds, None, 20., a)
+    vals, inds = vals.cpu().numpy(), inds.cpu().numpy()
+    x = torch.from_numpy(img).double()
+    # all patches of the video: P[t, y, x] = flattened pt x C x ps x ps patch
+    pat = x.unfold(0, pt, 1).unfold(2, ps, 1).unfold(3, ps, 1)          # [T-pt+1, C, H-ps+1, W-ps+1, pt, ps, ps]
+    pat = pat.permute(0, 2, 3, 1, 4, 5, 6).reshape(T - pt + 1, H - ps + 1, W - ps + 1, -1)
+    half = ws_ // 2
+    for qi, (t0, y0, x0) in enumerate(qs):
+        d = ((pat - pat[t0, y0, x0]) ** 2).sum(-1)                       # distances to every patch of the video
+        ok = torch.zeros_like(d, dtype=torch.bool)
+        if window_mode == "shift":                                       # windows keep their size, shifted into range
+            ta = min(max(t0 - nwt, 0), max(T - pt - 2 * nwt, 0)); tb = min(ta + 2 * nwt, T - pt)
+            ya = min(max(y0 - half, 0), H - ps - 2 * half); xa = min(max(x0 - half, 0), W - ps - 2 * half)
+            ok[ta:tb + 1, ya:ya + ws_, xa:xa + ws_] = True
+        else:                                                            # windows clipped at the borders
+            ok[max(t0 - nwt, 0):min(t0 + nwt, T - pt) + 1, max(y0 - half, 0):min(y0 + half, H - ps) + 1,
+               max(x0 - half, 0):min(x0 + half, W - ps) + 1] = True
+        d = torch.where(ok, d, torch.full_like(d, float("inf")))
+        best = torch.sort(d.flatten()).values[:k].numpy()
+        np.testing.assert_allclose(vals[qi], best, rtol=1e-5)
+        tt, yy, xx = inds[qi] // (C * H * W), (inds[qi] % (H * W)) // W, inds[qi] % W
+        assert bool(ok[tt, yy, xx].all())                                # every neighbour inside the window
+        dsel = d[tt, yy, xx].numpy()
+        np.testing.assert_allclose(dsel, vals[qi], rtol=1e-5)            # the reported distance belongs to the reported index
+        assert len(set(inds[qi].tolist())) == k
+
+
+@pytest.mark.parametrize("step,split", [(0, 1), (0, 0), (1, 1), (1, 0)])
+def test_bayes_covariance_and_eigenvalues_vs_oracle_and_reference(vb, golden_dir, step, split):
+    """North star: "per-group covariances ... to 1e-4 relative".  vnlb_bayes_debug exports what compute_cov_mat /
+    denoise_eigvals / bayes_filter_coeff (bayes_est.py:112-144) produce: the covariance (step 1) or the Gram matrix whose
+    non-zero spectrum is the covariance's (step 2, k = 60 < p = 98), the eigenvalues above the Wiener threshold and
+    their coefficients -- checked against the oracle AND the reference's own intermediates (bayes_parts_step*.npz).
+    Components whose eigenvalue straddles the threshold are counted and excluded explicitly."""
+    from vnlb_b200 import _lib, deno
+    from vnlb_b200.utils import AttrDict
+    g = np.load(os.path.join(golden_dir, "bayes_parts_step%d.npz" % (step + 1)))
+    a_gpu, a_cpu = gargs(vb, step), oargs(step)
+    pn, pb, flat = gin.bayes_inputs(step)
+    _, _, _, parts = orc.bayes_denoise(pn.copy(), pb.copy(), flat, a_cpu, return_parts=True)
+    prev = _lib.lib.vnlb_set_bayes_split(split)
+    try:
+        patches = AttrDict(noisy=cu(pn.copy()), basic=cu(pb.copy()), flat=cu(flat.astype(np.uint8)))
+        dbg = deno.bayes_debug(patches, a_gpu)
+    finally:
+        _lib.lib.vnlb_set_bayes_split(prev)
+    b, n, pt, c, ph, pw = pn.shape
+    mat = dbg["mat"].cpu().numpy().reshape(b * c, *dbg["mat"].shape[2:])
+    lam, coef, m = (dbg[k_].cpu().numpy().reshape(b * c, -1) for k_ in ("lam", "coef", "m"))
+    if not dbg["is_gram"]:
+        assert step == 0 and mat.shape[1] == 98
+        for i in range(b * c):
+            for ref in (parts["cov"][i], g["cov"][i]):
+                assert np.linalg.norm(mat[i] - ref) <= 1e-4 * np.linalg.norm(ref), i
+    else:                                             # Gram matrix of the centred basic patches, Y Y^T / n
+        assert step == 1 and mat.shape[1] == 60
+        Y = np.ascontiguousarray(pb.transpose(0, 3, 1, 2, 4, 5)).reshape(b * c, n, -1).astype(np.float64)
+        Y = Y - Y.mean(1, keepdims=True)
+        gram = np.matmul(Y, Y.transpose(0, 2, 1)) / n
+        for i in range(b * c):
+            assert np.linalg.norm(mat[i] - gram[i]) <= 1e-4 * np.linalg.norm(gram[i]), i
+            # its spectrum is the reference covariance's non-zero spectrum
+            ev = np.sort(np.linalg.eigvalsh(mat[i].astype(np.float64)))[::-1]
+            assert np.abs(ev[:39] - g["evals"][i, :39]).max() <= 1e-4 * g["evals"][i, 0], i
+    tau = a_cpu.thresh * a_cpu.sigma2 + a_cpu.sigmab2
+    nstraddle = 0
+    for i in range(b * c):
+        ref_l = g["evals"][i, :a_cpu.rank].astype(np.float64)
+        lmax = max(ref_l[0], 1e-20)
+        straddle = np.abs(ref_l - tau) <= 1e-4 * lmax
+        nstraddle += int(straddle.sum())
+        mref = int((ref_l > tau).sum())
+        if not straddle.any():
+            assert int(m[i, 0]) == mref, (i, m[i, 0], mref)
+        mm = min(int(m[i, 0]), mref)
+        assert np.abs(lam[i, :mm] - ref_l[:mm]).max(initial=0.) <= 1e-4 * lmax, i
+        assert np.abs(lam[i, :mm] - parts["evals"][i, :mm]).max(initial=0.) <= 1e-4 * lmax, i
+        keep = ~straddle[:mm]
+        assert np.abs(coef[i, :mm][keep] - g["coeff"][i, :mm][keep]).max(initial=0.) <= 1e-4, i
+        assert (lam[i, int(m[i, 0]):] == 0).all()
+    assert nstraddle == 0                             # none in these fixtures (reported, not silently skipped)
+    assert m.max() > 0
 
 
 def test_constant_video_is_a_fixed_point(vb):

@@ -82,11 +82,13 @@ def test_aggregation_bit_exact(golden_dir):
     np.testing.assert_array_equal(weights, g["weights"])
 
 
-def test_e2e_denoise(golden_dir):
-    """Whole vnlb.denoise: oracle vs the reference's own run (default_params),
-    tolerance of the north star: max-abs 1e-2, PSNR within 0.02 dB."""
-    g = _load(golden_dir, "e2e.npz")
-    e = gin.E2E
+@pytest.mark.parametrize("case", ["e2e", "e2e_s10", "e2e_s50", "e2e_cfg1"])
+def test_e2e_denoise(golden_dir, case):
+    """Whole vnlb.denoise: oracle vs the reference's own run (default_params) at sigma 20, at the noise levels of
+    BASELINE configs[4] (10 / 50) and on BASELINE configs[0] (3 x 64 x 64): tolerance of the north star,
+    max-abs 1e-2, PSNR within 0.02 dB."""
+    g = _load(golden_dir, case + ".npz")
+    e = gin.E2E_CASES[case]
     clean = orc.synth_video(e["T"], e["H"], e["W"], e["seed"])
     noisy = orc.add_noise(clean, e["sigma"], e["seed"])
     torch.manual_seed(e["torch_seed"])
@@ -95,4 +97,26 @@ def test_e2e_denoise(golden_dir):
     assert np.abs(deno - g["deno"]).max() < 1e-2
     ps = [orc.compute_psnrs(a, clean).mean() for a in (noisy, basic, deno)]
     np.testing.assert_allclose(ps, g["psnrs"], atol=0.02)
-    assert ps[2] > ps[1] > ps[0] + 8
+    assert ps[1] > ps[0] + 7 and ps[2] > ps[1]
+
+
+@pytest.mark.parametrize("step", [0, 1])
+def test_bayes_covariance_eigenvalues_coefficients(golden_dir, step):
+    """compute_cov_mat / denoise_eigvals / bayes_filter_coeff (bayes_est.py:112-144): the oracle's intermediates vs the
+    reference's (captured inside its own denoise call by make_golden.py): covariances to 1e-4 relative (north star),
+    the eigenvalues of the `rank` leading components to 1e-4 of the largest, coefficients to 1e-4 -- except components
+    whose eigenvalue straddles the Wiener threshold, which are counted and must be absent here."""
+    g = _load(golden_dir, "bayes_parts_step%d.npz" % (step + 1))
+    a = _args(step)
+    pn, pb, flat = gin.bayes_inputs(step)
+    _, _, _, parts = orc.bayes_denoise(pn, pb, flat, a, return_parts=True)
+    for i in range(g["cov"].shape[0]):
+        assert np.linalg.norm(parts["cov"][i] - g["cov"][i]) <= 1e-4 * np.linalg.norm(g["cov"][i]), i
+    lmax = g["evals"][:, :1]
+    assert np.abs(parts["evals"][:, :a.rank] - g["evals"][:, :a.rank]).max() <= 1e-4 * lmax.max()
+    assert (np.abs(parts["evals"][:, :a.rank] - g["evals"][:, :a.rank]) <= 1e-4 * lmax).all()
+    tau = a.thresh * a.sigma2 + a.sigmab2
+    straddle = np.abs(g["evals"][:, :a.rank] - tau) <= 1e-4 * lmax
+    assert straddle.sum() == 0                                    # none in these fixtures; they would be excluded below
+    np.testing.assert_allclose(parts["coeff"][:, :a.rank][~straddle], g["coeff"][:, :a.rank][~straddle], atol=1e-4)
+    assert (g["coeff"][:, :a.rank] > 0).any() and (g["coeff"][:, :a.rank] == 0).any()

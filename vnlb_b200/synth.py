@@ -6,12 +6,15 @@ translations, zero on the background)."""
 import numpy as np
 
 
-def synth_video(T, H, W, seed=123, C=3, return_flows=False):
+def synth_video(T, H, W, seed=123, C=3, return_flows=False, crop=None):
     rng = np.random.RandomState(seed)
-    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
-    vid = np.zeros((T, C, H, W), np.float32)
-    ff = np.zeros((T, 2, H, W), np.float32) if return_flows else None
-    bf = np.zeros((T, 2, H, W), np.float32) if return_flows else None
+    # crop = (Hc, Wc): only the top-left Hc x Wc corner of the H x W video is materialised (same content as cropping
+    # the full video; the CPU baseline's bounded sample of a 1080p workload)
+    Hc, Wc = (H, W) if crop is None else (min(int(crop[0]), H), min(int(crop[1]), W))
+    yy, xx = np.meshgrid(np.arange(Hc, dtype=np.float32), np.arange(Wc, dtype=np.float32), indexing="ij")
+    vid = np.zeros((T, C, Hc, Wc), np.float32)
+    ff = np.zeros((T, 2, Hc, Wc), np.float32) if return_flows else None
+    bf = np.zeros((T, 2, Hc, Wc), np.float32) if return_flows else None
     rects = []
     for _ in range(6):
         rh, rw = rng.randint(H // 6 + 2, H // 2 + 3), rng.randint(W // 6 + 2, W // 2 + 3)
@@ -27,7 +30,7 @@ def synth_video(T, H, W, seed=123, C=3, return_flows=False):
         for (y0, x0, rh, rw, vy, vx, tex) in rects:
             ya, xa = y0 + vy * t, x0 + vx * t
             ys, xs = max(0, ya), max(0, xa)
-            ye, xe = min(H, ya + rh), min(W, xa + rw)
+            ye, xe = min(Hc, ya + rh), min(Wc, xa + rw)
             if ye > ys and xe > xs:
                 vid[t, :, ys:ye, xs:xe] = tex[:, ys - ya:ye - ya, xs - xa:xe - xa]
                 if return_flows:     # the object's own translation (the last-drawn object wins, as in the frame)
