@@ -143,7 +143,8 @@ int vnlb_select_queries(int8_t *mask, int T, int H, int W, double prob, uint32_t
 /* Greedy conflict resolution inside a round of the throughput schedule (the reference resolves it by processing
  * sub-batches of 128 sequentially, lib/vnlb/search/search.py:38-64): after vnlb_search_topk and BEFORE
  * vnlb_mask_update, a row of `inds` whose reference pixel (its row of `qinds`) lies in the clear-set (found patches +
- * boost neighbours) of an EARLIER valid row of the same round is dropped -- its K indices become -1, so every later
+ * boost neighbours) of a valid row of the same round with a HIGHER PRIORITY (a hash of the reference pixel and the
+ * round: deterministic, unlike the row order) is dropped -- its K indices become -1, so every later
  * kernel skips it -- and its pixel is set in the mask again (a later round draws it if nothing ends up covering it).
  * owner: uint32 [T,H,W] scratch, filled with 0xFFFFFFFF once per step by the caller; round: 0, 1, ... within the step
  * (stamps carry the round, the map is never cleared in between); dropped: uint32 counter, incremented. */

@@ -302,6 +302,21 @@ def test_e2e_parity_schedule_vs_golden_and_oracle(vb, golden_dir, case):
         assert dt > 0
 
 
+# ---------------------------------------------------------------- Bayes: stress and odd shapes
+def _stress_stack(rs, n, ps, pt, scale, sigma=20., c=3, b=4):
+    p = pt * ps * ps
+    s2 = sigma * sigma
+    out = np.zeros((b, c, n, p), np.float32)
+    for g in range(b):
+        for ch in range(c):
+            basis = np.linalg.qr(rs.randn(p, 3))[0]
+            coef = rs.randn(n, 3) * np.sqrt(s2 * scale) * np.array([1., .5, .25])
+            out[g, ch] = coef @ basis.T + rs.randn(n, p) * sigma + rs.rand(1, p) * 100
+    return np.ascontiguousarray(out.reshape(b, c, n, pt, ps, ps).transpose(0, 2, 3, 1, 4, 5)).astype(np.float32)
+
+
+@pytest.mark.parametrize("scale,thresh,step", [(600., 2.7, 0), (600., 1.5, 0), (5000., 2.7, 0), (600., 0.7, 1),
+                                               (50., 0.3, 1), (0.0, 0.3, 1)])
 def test_bayes_tridiag_clustered_eigenvalues(vb, scale, thresh, step):
     """Many (up to rank = 39) tightly clustered noise eigenvalues above the threshold."""
     from vnlb_b200 import deno

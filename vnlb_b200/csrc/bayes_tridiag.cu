@@ -530,6 +530,187 @@ __device__ __forceinline__ void tridiag_regs(float2 (&b)[2 * NRC], float *sv, fl
     (void)LDG;
 }
 
+// ---------------------------------------------------------------------------------------------
+// TWO ROWS PER THREAD, one warp per problem (NR <= 64): lane l owns rows l and l + 32 of the trailing matrix.  The sweep
+// of tridiag_regs is bound by the shared-memory data pipe: per 4 columns a warp loads 3 broadcast LDS.128 (v, w, next x)
+// for 6 FFMA2 of ONE row per lane (measured: 0.42 LDS.128 against 1.72 FFMA2 per cycle and SM, 2 : 1 load bound).  With
+// two rows per lane the same three loads feed 12 FFMA2 and a problem needs half the warps, so the phase is balanced
+// between the two pipes; and since one warp holds the whole problem, the two named barriers of a step become
+// __syncwarp(), the block reduction becomes a shuffle tree and the scalars of rows c, c-1, c-2 come from their
+// owners by shuffle instead of through shared memory.  Same arithmetic per element as tridiag_regs (operation order
+// of the update and of the raw-column trick unchanged); only the order of the partial sums of a mat-vec differs.
+// Shared scratch (floats): 2 x xs (ping-pong), vs, ws, then d, e, tau (KN each) and the packed reflectors.
+template <int QDG, int NR, int CEND> __host__ __device__ constexpr int tridiag2_scratch_floats() {
+    return 4 * (((NR + 3) & ~3) + 4) + 3 * ((NR - CEND + 5) & ~3) + ((refl_off(QDG, QDG - CEND) - refl_off(QDG, QDG - NR) + 3) & ~3);
+}
+
+template <int QDG, int NR, int CEND, int OPITCH, int OREFL>
+__device__ __forceinline__ void tridiag_regs2(float2 (&bl)[2 * ((NR + 3) / 4)], float2 (&bh)[2 * ((NR + 3) / 4)], float *sv,
+                                              float *out, float *trail, int lane) {
+    constexpr int LDQ = (NR + 3) & ~3, NCH = LDQ / 4, VL = LDQ + 4;
+    constexpr int K0 = QDG - NR, K1 = QDG - 1 - CEND;
+    constexpr int KN = (K1 - K0 + 1 + 2 + 3) & ~3;
+    constexpr int R0 = refl_off(QDG, K0), R1 = refl_off(QDG, K1 + 1);
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(NR > 32 && NR <= 64 && CEND >= 32 && CEND < NR && CEND % 4 == 0, "tridiag_regs2: 32 < NR <= 64, the rest handed on is 32 x 32 or larger");
+    auto coll = [&](auto jc) -> float { constexpr int j = decltype(jc)::value; return (j & 1) ? bl[j >> 1].y : bl[j >> 1].x; };
+    auto colh = [&](auto jc) -> float { constexpr int j = decltype(jc)::value; return (j & 1) ? bh[j >> 1].y : bh[j >> 1].x; };
+    const uint32_t s0 = smem_u32(sv);
+    const uint32_t aV = s0 + 8 * VL, aW = s0 + 12 * VL;                       // byte addresses
+    const uint32_t aD = s0 + 16 * VL, aE = aD + 4 * KN, aTau = aE + 4 * KN, aRefl = aTau + 4 * KN;
+    const int i0 = lane, i1 = lane + 32;
+    for (int j = lane; j < 4 * VL; j += 32) sv[j] = 0.f;
+    __syncwarp();
+    constexpr int c0 = NR - 1;
+    // row c's owner: lane c & 31, its upper row when c >= 32 (c is warp uniform)
+    auto from_row = [&](int row, float lo, float hi) -> float { return __shfl_sync(FULL, row >= 32 ? hi : lo, row & 31); };
+    float xl, xh, rl, rh, yl = 0.f, yh = 0.f, dk;
+    {
+        const float x0l = coll(std::integral_constant<int, c0>()), x0h = colh(std::integral_constant<int, c0>());
+        rl = coll(std::integral_constant<int, c0 - 1>());
+        rh = colh(std::integral_constant<int, c0 - 1>());
+        if (i0 < c0) sts32(s0 + 4 * i0, x0l);
+        if (i1 < c0) sts32(s0 + 4 * i1, x0h);
+        dk = from_row(c0, x0l, x0h);                                          // B[c0][c0]
+        xl = i0 < c0 ? x0l : 0.f;
+        xh = i1 < c0 ? x0h : 0.f;
+    }
+    int Iw = (c0 - 2) >> 2;                                                    // the windows hold columns 4 Iw .. 4 Iw + 3 of both rows
+    constexpr int w0 = 4 * ((c0 - 2) >> 2);
+    float wl0 = coll(std::integral_constant<int, w0>()), wl1 = coll(std::integral_constant<int, w0 + 1>());
+    float wl2 = coll(std::integral_constant<int, w0 + 2>()), wl3 = coll(std::integral_constant<int, w0 + 3>());
+    float wh0 = colh(std::integral_constant<int, w0>()), wh1 = colh(std::integral_constant<int, w0 + 1>());
+    float wh2 = colh(std::integral_constant<int, w0 + 2>()), wh3 = colh(std::integral_constant<int, w0 + 3>());
+    __syncwarp();
+    {   // y = B x for the first column, both rows
+        float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#pragma unroll
+        for (int I = 0; I < NCH; ++I) {
+            const float4 x4 = lds128(s0 + 16 * I);
+            a0 = __ffma2_rn(bl[2 * I], make_float2(x4.x, x4.y), a0); a1 = __ffma2_rn(bl[2 * I + 1], make_float2(x4.z, x4.w), a1);
+            b0 = __ffma2_rn(bh[2 * I], make_float2(x4.x, x4.y), b0); b1 = __ffma2_rn(bh[2 * I + 1], make_float2(x4.z, x4.w), b1);
+        }
+        yl = (a0.x + a0.y) + (a1.x + a1.y);
+        yh = (b0.x + b0.y) + (b1.x + b1.y);
+    }
+    for (int c = NR - 1; c >= CEND; --c) {
+        const int k = NR - 1 - c;
+        const int nb2 = (c + 7) >> 3;
+        const uint32_t pp = k & 1;
+        const uint32_t aXn = s0 + (pp ^ 1) * (4 * VL);
+        __syncwarp();                                                          // the previous sweep's reads of v, w, x are done
+        const float xBx = warp_sum(fmaf(xh, yh, xl * yl));                     // x = 0 on rows >= c
+        const float yc = from_row(c, yl, yh), ycm1 = from_row(c - 1, yl, yh), ycm2 = from_row(c - 2, yl, yh);
+        const float alpha = from_row(c - 1, xl, xh), bcc = from_row(c - 1, rl, rh);
+        const float xcm2 = from_row(c - 2, xl, xh), rcm2 = from_row(c - 2, rl, rh);
+        const float a2 = alpha * alpha;
+        const float nrm2 = fmaxf(yc, a2);
+        const bool skip = (nrm2 == a2);
+        const float rsq = rsqrt_approx(nrm2);
+        float sq = nrm2 * rsq;
+        sq = fmaf(0.5f * rsq, fmaf(-sq, sq, nrm2), sq);
+        const float beta = skip ? alpha : -copysignf(sq, alpha);
+        const float tau = skip ? 0.f : (beta - alpha) * rcp_newton(beta);
+        const float scale = skip ? 0.f : rcp_newton(alpha - beta);
+        const float ts = tau * scale;
+        const float uBu = fmaf(beta * beta, bcc, fmaf(-2.f * beta, ycm1, xBx));
+        const float hs = 0.5f * ts * ts * uBu;
+        const float wcm1 = fmaf(-hs, 1.f, ts * fmaf(-beta, bcc, ycm1));
+        const float vcm2 = xcm2 * scale;
+        const float wcm2 = fmaf(-hs, vcm2, ts * fmaf(-beta, rcm2, ycm2));
+        const int wsel = (c - 2) & 3;
+        const bool actl = i0 < c, acth = i1 < c;
+        float vl = (i0 == c - 1) ? 1.f : xl * scale, vh = (i1 == c - 1) ? 1.f : xh * scale;
+        float wl = fmaf(-hs, vl, ts * fmaf(-beta, rl, yl)), wh = fmaf(-hs, vh, ts * fmaf(-beta, rh, yh));
+        if (!actl) { vl = 0.f; wl = 0.f; }                                     // dead rows: the update is a no-op
+        if (!acth) { vh = 0.f; wh = 0.f; }
+        const float ql = wsel == 0 ? wl0 : (wsel == 1 ? wl1 : (wsel == 2 ? wl2 : wl3));
+        const float qh = wsel == 0 ? wh0 : (wsel == 1 ? wh1 : (wsel == 2 ? wh2 : wh3));
+        const float xnl = fmaf(-vl, wcm1, fmaf(-wl, 1.f, rl)), xnh = fmaf(-vh, wcm1, fmaf(-wh, 1.f, rh));
+        const float rnl = fmaf(-vl, wcm2, fmaf(-wl, vcm2, ql)), rnh = fmaf(-vh, wcm2, fmaf(-wh, vcm2, qh));
+        if (actl) {
+            sts32(aV + 4 * i0, vl); sts32(aW + 4 * i0, wl);
+            sts32(aRefl + 4 * (refl_off(QDG, K0 + k) - R0 + (c - 1 - i0)), vl);
+            sts32(aXn + 4 * i0, (i0 < c - 1) ? xnl : 0.f);
+        }
+        if (acth) {
+            sts32(aV + 4 * i1, vh); sts32(aW + 4 * i1, wh);
+            sts32(aRefl + 4 * (refl_off(QDG, K0 + k) - R0 + (c - 1 - i1)), vh);
+            sts32(aXn + 4 * i1, (i1 < c - 1) ? xnh : 0.f);
+        }
+        if (i0 == c) sts32(aXn + 4 * i0, 0.f);
+        if (i1 == c) sts32(aXn + 4 * i1, 0.f);
+        if (lane == 0) { sts32(aD + 4 * k, dk); sts32(aE + 4 * k, beta); sts32(aTau + 4 * k, tau); }
+        dk = from_row(c - 1, xnl, xnh);                                        // B[c-1][c-1] after the update: the next diagonal entry
+        __syncwarp();
+        {
+            const float2 nvl = make_float2(-vl, -vl), nwl = make_float2(-wl, -wl);
+            const float2 nvh = make_float2(-vh, -vh), nwh = make_float2(-wh, -wh);
+            float2 a0 = make_float2(0.f, 0.f), a1 = a0, b0 = a0, b1 = a0;
+#define VNLB_S2(J)                                                                       \
+            if constexpr ((J) < NCH) {                                                  \
+                constexpr int I = (J) < NCH ? (J) : 0;                                  \
+                const float4 v4 = lds128(aV + 16 * I), w4 = lds128(aW + 16 * I), x4 = lds128(aXn + 16 * I);                       \
+                const float2 v01 = make_float2(v4.x, v4.y), v23 = make_float2(v4.z, v4.w);                                          \
+                const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);                                          \
+                const float2 x01 = make_float2(x4.x, x4.y), x23 = make_float2(x4.z, x4.w);                                          \
+                bl[2 * I] = __ffma2_rn(nvl, w01, __ffma2_rn(nwl, v01, bl[2 * I]));                                                  \
+                bl[2 * I + 1] = __ffma2_rn(nvl, w23, __ffma2_rn(nwl, v23, bl[2 * I + 1]));                                          \
+                bh[2 * I] = __ffma2_rn(nvh, w01, __ffma2_rn(nwh, v01, bh[2 * I]));                                                  \
+                bh[2 * I + 1] = __ffma2_rn(nvh, w23, __ffma2_rn(nwh, v23, bh[2 * I + 1]));                                          \
+                a0 = __ffma2_rn(bl[2 * I], x01, a0); a1 = __ffma2_rn(bl[2 * I + 1], x23, a1);                                       \
+                b0 = __ffma2_rn(bh[2 * I], x01, b0); b1 = __ffma2_rn(bh[2 * I + 1], x23, b1);                                       \
+            }
+#define VNLB_S2B(G) case (G) + 1: { VNLB_S2(2 * (G) + 1) VNLB_S2(2 * (G)) }
+            switch (nb2) {
+                VNLB_S2B(7) VNLB_S2B(6) VNLB_S2B(5) VNLB_S2B(4) VNLB_S2B(3) VNLB_S2B(2) VNLB_S2B(1) VNLB_S2B(0)
+                default: break;
+            }
+#undef VNLB_S2B
+#undef VNLB_S2
+            yl = (a0.x + a0.y) + (a1.x + a1.y);
+            yh = (b0.x + b0.y) + (b1.x + b1.y);
+            {   // the window copies get the same update
+                const float4 v4 = lds128(aV + 16 * Iw), w4 = lds128(aW + 16 * Iw);
+                wl0 = fmaf(-vl, w4.x, fmaf(-wl, v4.x, wl0)); wl1 = fmaf(-vl, w4.y, fmaf(-wl, v4.y, wl1));
+                wl2 = fmaf(-vl, w4.z, fmaf(-wl, v4.z, wl2)); wl3 = fmaf(-vl, w4.w, fmaf(-wl, v4.w, wl3));
+                wh0 = fmaf(-vh, w4.x, fmaf(-wh, v4.x, wh0)); wh1 = fmaf(-vh, w4.y, fmaf(-wh, v4.y, wh1));
+                wh2 = fmaf(-vh, w4.z, fmaf(-wh, v4.z, wh2)); wh3 = fmaf(-vh, w4.w, fmaf(-wh, v4.w, wh3));
+            }
+        }
+        if (((c - 3) >> 2) != Iw) {                                            // next step needs column c-3: re-read the windows from the registers
+            Iw = (c - 3) >> 2;
+            switch (Iw) {
+#define VNLB_W2(J) case (J): if constexpr ((J) < NCH) { constexpr int I = (J) < NCH ? (J) : 0; wl0 = bl[2 * I].x; wl1 = bl[2 * I].y; wl2 = bl[2 * I + 1].x; wl3 = bl[2 * I + 1].y; \
+                                                        wh0 = bh[2 * I].x; wh1 = bh[2 * I].y; wh2 = bh[2 * I + 1].x; wh3 = bh[2 * I + 1].y; } break;
+                VNLB_W2(0) VNLB_W2(1) VNLB_W2(2) VNLB_W2(3) VNLB_W2(4) VNLB_W2(5) VNLB_W2(6) VNLB_W2(7) VNLB_W2(8) VNLB_W2(9) VNLB_W2(10) VNLB_W2(11)
+                VNLB_W2(12) VNLB_W2(13) VNLB_W2(14) VNLB_W2(15)
+#undef VNLB_W2
+                default: break;
+            }
+        }
+        xl = (i0 < c - 1) ? xnl : 0.f;
+        xh = (i1 < c - 1) ? xnh : 0.f;
+        rl = rnl;
+        rh = rnh;
+    }
+    {   // trailing CEND x CEND matrix for the next phase: row t at trail + t * CEND (CEND = 32: the lower rows only)
+        static_assert(CEND == 32, "tridiag_regs2 hands a 32 x 32 matrix on");
+#pragma unroll
+        for (int I = 0; I < CEND / 4; ++I)
+            reinterpret_cast<float4 *>(trail + lane * CEND)[I] = make_float4(bl[2 * I].x, bl[2 * I].y, bl[2 * I + 1].x, bl[2 * I + 1].y);
+    }
+    __syncwarp();
+    constexpr int NK = K1 - K0 + 1;
+    const float *sd = sv + 4 * VL;
+    for (int idx = lane; idx < NK; idx += 32) {
+        out[K0 + idx] = sd[idx];
+        out[OPITCH + K0 + idx] = sd[KN + idx];
+        out[2 * OPITCH + K0 + idx] = sd[2 * KN + idx];
+    }
+    for (int idx = lane; idx < R1 - R0; idx += 32) out[OREFL + R0 + idx] = sd[3 * KN + idx];
+}
+
 // Workspace per problem (floats): d[LDG] e[LDG] tau[LDG] mean[LDG] reflectors[nref] trailing matrix[NR2 x NR2];
 // tau[LDG-1] doubles as the "problem is valid" flag between the kernels of the split path.
 constexpr int SPLIT_NR2 = 64;                      // trailing size handed from phase 1 to phase 2
@@ -738,6 +919,31 @@ __global__ void __launch_bounds__(NT, OCC) tridiag_tail_kernel(const BayesArgs a
     tridiag_regs<QDG, NR, CEND, NT, NCH, OPITCH, OREFL>(b, sm, wsp, wsp + TOUT, tid);
 }
 
+
+// Two-rows-per-thread version of a tail phase (tridiag_regs2): ONE warp per problem, the NR x NR trailing matrix (row pitch
+// NR at float offset TIN of the problem's workspace) -> columns NR-1 .. 32 eliminated -> the 32 x 32 rest at TOUT.
+template <int QDG, int NR, int OCC, int OPITCH, int OREFL, int TIN, int TOUT>
+__global__ void __launch_bounds__(32, OCC) tridiag_tail2_kernel(const BayesArgs a) {
+    constexpr int NCH = (NR + 3) / 4;
+    static_assert(NR % 4 == 0, "tridiag_tail2_kernel: NR a multiple of 4");
+    extern __shared__ __align__(16) float sm[];
+    float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
+    if (wsp[3 * OPITCH - 1] == 0.f) return;           // group skipped by the first kernel
+    const int lane = threadIdx.x;
+    float2 bl[2 * NCH], bh[2 * NCH];
+    const float4 *trl = reinterpret_cast<const float4 *>(wsp + TIN + lane * NR);
+    const float4 *trh = reinterpret_cast<const float4 *>(wsp + TIN + min(lane + 32, NR - 1) * NR);
+    const float live = lane + 32 < NR ? 1.f : 0.f;
+#pragma unroll
+    for (int I = 0; I < NCH; ++I) {
+        const float4 f = trl[I], g = trh[I];
+        bl[2 * I] = make_float2(f.x, f.y);
+        bl[2 * I + 1] = make_float2(f.z, f.w);
+        bh[2 * I] = make_float2(g.x * live, g.y * live);
+        bh[2 * I + 1] = make_float2(g.z * live, g.w * live);
+    }
+    tridiag_regs2<QDG, NR, 32, OPITCH, OREFL>(bl, bh, sm, wsp, wsp + TOUT, lane);
+}
 
 // Split path of the Gram variant (step 2: n = 60 patches < p = 98 elements): centre + Gram matrix G = Yc Yc^T / n +
 // its whole tridiagonalisation, one CTA of 64 threads per (group, channel) problem, 8 CTAs per SM.  Same structure as
@@ -1748,6 +1954,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
 
 // Split path (cov_tridiag_kernel + bayes_kernel<.., SPLIT>) for the production shape of step 1 (7x7x2 patches: q = 98,
 // direct covariance); VNLB_BAYES_SPLIT=0 forces the single-kernel shared-memory path.
+static int g_tail2 = []() { const char *s = getenv("VNLB_TAIL2"); return (s && s[0] == '0') ? 0 : 1; }();   // VNLB_TAIL2=0: one row per thread in the 64 -> 32 phase (A/B measurements)
 static int g_split = -1;   // -1: not read yet; VNLB_BAYES_SPLIT=0 in the environment or vnlb_set_bayes_split(0) disables
 static bool use_split(const TriLayout &L) {
     if (g_split < 0) { const char *s = getenv("VNLB_BAYES_SPLIT"); g_split = (s && s[0] == '0') ? 0 : 1; }
@@ -1861,7 +2068,12 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
         k1<<<B * p->c, TT, smem1, st>>>(a);
-        k1b<<<B * p->c, 64, smem1b, st>>>(a);
+        if (g_tail2) {      // phase 64 -> 32 with two rows per thread, one warp per problem
+            auto k1b2 = tridiag_tail2_kernel<QD, SPLIT_NR2, 10, LDG, 4 * LDG, split_trail_off<QD>(), split_trail2_off<QD>()>;
+            k1b2<<<B * p->c, 32, (size_t)tridiag2_scratch_floats<QD, SPLIT_NR2, SPLIT_NR3>() * sizeof(float), st>>>(a);
+        } else {
+            k1b<<<B * p->c, 64, smem1b, st>>>(a);
+        }
         k1c<<<B * p->c, 32, smem1c, st>>>(a);
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
         return check_launch(what, 4);

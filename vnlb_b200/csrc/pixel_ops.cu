@@ -182,17 +182,25 @@ __global__ void pad_queries_kernel(long long *__restrict__ qinds, const unsigned
 // sequentially in sub-batches of 128 and every sub-batch clears what it found before the next one is drawn
 // (search.py:38-64), so a pixel covered by an earlier group is never processed.  A round of this schedule draws
 // thousands of pixels at once; without this step two drawn pixels that cover each other are both processed
-// (+9..13 % groups, profiles/r1b).  Pass 1: every valid row i stamps owner[pixel] = min(owner, key(round, i)) at
-// each pixel its group would clear (found patches + the 4 boost neighbours).  Pass 2: row j is dropped (its
-// indices set to -1) when the stamp on its own reference pixel comes from a row i < j of the same round; its pixel
-// goes back into the mask, so if the group that covered it is dropped as well it is drawn again in a later round.
-// key = (65535 - round) << 15 | row: later rounds always win the atomicMin over stale stamps, no clearing needed.
+// (+9..13 % groups, profiles/r1b).  Every row gets a PRIORITY, a 15-bit hash of its reference pixel (the row order
+// itself comes from atomics and differs from run to run; the hash keeps the schedule deterministic).  Pass 1: every
+// valid row stamps owner[pixel] = min(owner, key(round, priority)) at each pixel its group would clear (found
+// patches + the 4 boost neighbours).  Pass 2: a row is dropped (its indices set to -1) when the stamp on its own
+// reference pixel carries a SMALLER priority of the same round (equal priorities never drop each other); its
+// pixel goes back into the mask, so if the group that covered it is dropped as well it is drawn again later.
+// key = (65535 - round) << 15 | priority: later rounds always win the atomicMin over stale stamps, no clearing needed.
 // ---------------------------------------------------------------------------
-__global__ void round_stamp_kernel(const long long *__restrict__ inds, int K, unsigned int *__restrict__ owner,
-                                   unsigned int round_key, int T, int C, int H, int W, int boost) {
+__device__ __forceinline__ unsigned int row_priority(const long long *q, int H, int W, unsigned int round) {
+    const long long pix = (q[0] * H + q[1]) * W + q[2];
+    return hash3((unsigned)pix, (unsigned)(pix >> 32) ^ 0x51ED27u, round) & 0x7fffu;
+}
+
+__global__ void round_stamp_kernel(const long long *__restrict__ qinds, const long long *__restrict__ inds, int K,
+                                   unsigned int *__restrict__ owner, unsigned int round_key, unsigned int round, int T,
+                                   int C, int H, int W, int boost) {
     const long long *row = inds + (long long)blockIdx.x * K;
     if (!row_valid_block(row, K)) return;
-    const unsigned int key = round_key | blockIdx.x;
+    const unsigned int key = round_key | row_priority(qinds + 3 * (long long)blockIdx.x, H, W, round);
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
         int t, y, x;
         decode_ind(row[i], H, W, C, t, y, x);
@@ -209,15 +217,16 @@ __global__ void round_stamp_kernel(const long long *__restrict__ inds, int K, un
 }
 
 __global__ void round_drop_kernel(const long long *__restrict__ qinds, long long *__restrict__ inds, int B, int K,
-                                  const unsigned int *__restrict__ owner, unsigned int round_key,
+                                  const unsigned int *__restrict__ owner, unsigned int round_key, unsigned int round,
                                   int8_t *__restrict__ mask, int T, int H, int W, unsigned int *__restrict__ dropped) {
     const int j = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= B) return;
-    const long long t = qinds[3 * (long long)j], y = qinds[3 * (long long)j + 1], x = qinds[3 * (long long)j + 2];
+    const long long *q = qinds + 3 * (long long)j;
+    const long long t = q[0], y = q[1], x = q[2];
     if (t < 0 || t >= T || y < 0 || y >= H || x < 0 || x >= W) return;
     const long long pix = (t * H + y) * W + x;
     const unsigned int o = owner[pix];
-    if ((o & ~0x7fffu) != round_key || (o & 0x7fffu) >= (unsigned)j) return;   // not covered by an earlier row of this round
+    if ((o & ~0x7fffu) != round_key || (o & 0x7fffu) >= row_priority(q, H, W, round)) return;   // not covered by a higher-priority row of this round
     long long *row = inds + (long long)j * K;
     if (row[0] < 0) return;                                                     // already invalid
     for (int i = lane; i < K; i += 32) row[i] = -1;
@@ -235,9 +244,10 @@ extern "C" int vnlb_round_dedup(const int64_t *qinds, int64_t *inds, int B, int 
     VNLB_REQUIRE(B <= 32768 && round < 65535u, "vnlb_round_dedup: at most 32768 rows per round and 65535 rounds");
     if (B == 0) return VNLB_OK;
     const unsigned int key = (65535u - round) << 15;
-    round_stamp_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const long long *)inds, K, owner, key, T, C, H, W, boost);
+    round_stamp_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const long long *)qinds, (const long long *)inds, K, owner, key,
+                                                            round, T, C, H, W, boost);
     round_drop_kernel<<<div_up(B, 8), 256, 0, (cudaStream_t)stream>>>((const long long *)qinds, (long long *)inds, B, K,
-                                                                     owner, key, mask, T, H, W, dropped);
+                                                                     owner, key, round, mask, T, H, W, dropped);
     return check_launch("vnlb_round_dedup", 2);
 }
 
