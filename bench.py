@@ -201,13 +201,17 @@ def run_ours(args):
     flows_pin = dict(fflow=pin(flows_np["fflow"]), bflow=pin(flows_np["bflow"]))
     noisy_dev = noisy_pin.to(device)
     flows_dev = dict(fflow=flows_pin["fflow"].to(device), bflow=flows_pin["bflow"].to(device))
-    out_pin = torch.empty_like(noisy_pin).pin_memory() if rank == 0 else None
+    if world == 1:
+        out_pin = torch.empty_like(noisy_pin).pin_memory()
+    else:       # every rank reads back its own band of the estimate (the output stays sharded like the work)
+        out_pin = torch.empty((T * 3 * (H // world + H // (4 * world) + 16) * W,), dtype=torch.float32).pin_memory()
     del flows_np
 
-    def call(x, fl, sigma=SIGMA, stats=None, params=None):
+    def call(x, fl, sigma=SIGMA, stats=None, params=None, gather=True):
         params = params if params is not None else vnlb_b200.get_params(sigma)
         if world > 1:
-            return vdist.denoise_distributed(x, sigma, flows=fl, params=params, stats=stats, device=device, max_flow=MAX_FLOW)
+            return vdist.denoise_distributed(x, sigma, flows=fl, params=params, stats=stats, device=device, max_flow=MAX_FLOW,
+                                             gather=gather)
         return vnlb_b200.denoise(x, sigma, gpuid=local_rank, verbose=False, flows=fl, schedule="fast", params=params, stats=stats)
 
     def barrier():
@@ -261,9 +265,12 @@ def run_ours(args):
     st_e2e = {}
 
     def step_e2e():
-        d, _, _ = call(noisy_pin, flows_pin, stats=st_e2e)
-        if rank == 0:
+        if world == 1:
+            d, _, _ = call(noisy_pin, flows_pin, stats=st_e2e)
             out_pin.copy_(d, non_blocking=True)
+        else:
+            d, _, _ = call(noisy_pin, flows_pin, stats=st_e2e, gather=False)
+            out_pin[:d.numel()].copy_(d.reshape(-1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     for _ in range(min(args.warmup, 2)):
@@ -303,7 +310,8 @@ def run_ours(args):
         per_rank = dict(groups=[int(a[0].item()) for a in allr], stage_ms=[round(float(a[1].item()), 1) for a in allr],
                         value_step_ms=[[round(float(x), 1) for x in a.tolist()] for a in all_steps],
                         exchange_ms_rank0=[round(x, 2) for x in st2.get("exchange_ms", [])],
-                        exchange_bytes_rank0=st2.get("exchange_bytes"), layout_rank0=st2.get("layout"))
+                        exchange_bytes_rank0=st2.get("exchange_bytes"), layout_rank0=st2.get("layout"),
+                        rebalance_rank0=st2.get("rebalance"))
 
     if rank == 0:
         hbm_peak, hbm_kind, fp32_peak, fp32_kind, fp32_rec = load_peaks()
@@ -384,7 +392,9 @@ def run_ours(args):
                         l2="working set (noisy + flows + basic + accumulators ~%.1f GB) exceeds the 126 MB L2" % (T * H * W * 4 * 14 / 1e9)),
             e2e=dict(value=mpx * args.steps / (ms_e2e / 1e3), unit="Mpx/s", ms_per_step=ms_e2e / args.steps,
                      h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=int(noisy.nbytes),
-                     note="video + forward/backward flows host->device (each rank its band + halo rows only), estimate device->host on rank 0"),
+                     note="video + forward/backward flows host->device (each rank its band + halo rows only); estimate device->host, at "
+                          "N > 1 every rank its own band (the output stays sharded like the work; `value` includes the all-gather "
+                          "that gives every rank the full frames)"),
             sigma50=dict(value=mpx * n_alt / (ms_alt / 1e3), unit="Mpx/s", ms_per_step=ms_alt / n_alt, steps=n_alt,
                          groups_per_step=[int(g) for g in st_alt.get("ngroups", [])][-2:], psnr=psnr_alt),
             gpu_launches=int(launches), clocks=clocks, roofline=roof, search=srch, cpu_baseline=cpu,

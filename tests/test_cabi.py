@@ -68,7 +68,7 @@ def test_bayes_workspace_contract_without_a_gpu():
     try:
         b1 = int(_lib.lib.vnlb_bayes_workspace_bytes(1, ctypes.byref(p1)))
         b2 = int(_lib.lib.vnlb_bayes_workspace_bytes(1, ctypes.byref(p2)))
-        assert 30_000 * 3 < b1 < 45_000 * 3 and 10_000 * 3 < b2 < 18_000 * 3          # ~41 KB / ~12-16 KB per (group, channel)
+        assert 30_000 * 3 < b1 < 45_000 * 3 and 10_000 * 3 < b2 < 30_000 * 3          # ~41 KB / ~27 KB per (group, channel)
         assert int(_lib.lib.vnlb_bayes_workspace_bytes(1000, ctypes.byref(p1))) == 1000 * b1
         assert int(_lib.lib.vnlb_bayes_workspace_bytes(10 ** 6, ctypes.byref(p1))) == 16384 * b1   # chunked beyond a round
         p3 = _lib.BayesParams(0, 40, 5, 1, 3, 20, 400., 400., 2.7, 0, _lib.EIG_TRIDIAG)           # other shapes: single kernel

@@ -73,6 +73,70 @@ def test_halo_and_exchange_plan():
             assert plans[s][1][r] == rows
 
 
+def test_rebalanced_cuts_equalise_predicted_time_within_the_margin():
+    """Host arithmetic of the mid-step load balancing: equal speeds and equal remaining work leave the borders alone; a
+    slow rank gives rows away; borders never move more than `margin` rows from the layout and bands never vanish."""
+    from vnlb_b200.dist import partition_rows, rebalanced_cuts
+    h, ps, world, margin = 1080, 7, 8, 14
+    bands = [partition_rows(h, ps, world, r) for r in range(world)]
+    rem = np.full(h, 1000.0)
+    rem[h - ps + 1:] = 0
+    same = rebalanced_cuts(rem, [50.0] * world, bands, bands, margin, ps)
+    assert all(abs(a[0] - b[0]) <= 1 for a, b in zip(same, bands))
+    speeds = [50.0] * world
+    speeds[3] = 40.0                                            # rank 3 is 20 % slower: it must shrink
+    new = rebalanced_cuts(rem, speeds, bands, bands, margin, ps)
+    assert new[0][0] == 0 and new[-1][1] == h
+    for a, b in zip(new[:-1], new[1:]):
+        assert a[1] == b[0] and a[1] - a[0] >= ps
+    assert (new[3][1] - new[3][0]) < (bands[3][1] - bands[3][0])
+    assert all(abs(n[0] - o[0]) <= margin for n, o in zip(new, bands))
+    t_old = [rem[a:b].sum() / speeds[r] for r, (a, b) in enumerate(bands)]
+    t_new = [sum(rem[y] / speeds[[r for r, (a, b) in enumerate(bands) if a <= y < b][0]] for y in range(a2, b2))
+             for (a2, b2) in new]
+    assert max(t_new) < max(t_old)                             # the slowest rank finishes earlier
+    # a second rebalance starts from the moved bands but stays inside the margin of the ORIGINAL layout
+    again = rebalanced_cuts(rem, speeds, new, bands, margin, ps)
+    assert all(abs(n[0] - o[0]) <= margin for n, o in zip(again, bands))
+    # degenerate: nothing left anywhere
+    assert rebalanced_cuts(np.zeros(h), speeds, bands, bands, margin, ps) == bands
+
+
+def _migrate_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from vnlb_b200.dist import BandRebalancer, make_layout
+    T, H, W, halo, margin = 2, 60, 8, 5, 4
+    bands, tiles = make_layout(H, 7, world, halo, None, margin)
+    ya, yb = tiles[rank]
+    glob = (np.random.RandomState(1).rand(T, H, W) < 0.5).astype(np.int8)      # the "current" global mask state
+    mask = torch.zeros((T, yb - ya, W), dtype=torch.int8)
+    y0, y1 = bands[rank]
+    mask[:, y0 - ya:y1 - ya] = torch.from_numpy(glob[:, y0:y1])
+    reb = BandRebalancer(bands, tiles, rank, None, margin, H, W, T, 7, 2, 3)
+    new = [(0, bands[0][1] + 3), (bands[0][1] + 3, H)] if world == 2 else \
+        [(0, bands[0][1] - 2), (bands[0][1] - 2, bands[1][1] + 4), (bands[1][1] + 4, H)]
+    reb._migrate(mask, new)
+    n0, n1 = new[rank]
+    ok = np.array_equal(mask[:, n0 - ya:n1 - ya].numpy(), glob[:, n0:n1])       # my new band carries the current state
+    outside = mask.clone()
+    outside[:, n0 - ya:n1 - ya] = 0
+    out["ok_%d" % rank] = bool(ok) and int(outside.abs().sum()) == 0              # and nothing is set outside it
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("world", [2, 3])
+def test_mask_rows_follow_the_moving_borders(world):
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_migrate_worker, args=(world, port, out), nprocs=world, join=True)
+        assert all(out["ok_%d" % r] for r in range(world)), dict(out)
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

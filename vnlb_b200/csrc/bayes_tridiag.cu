@@ -952,9 +952,12 @@ __global__ void __launch_bounds__(32, OCC) tridiag_tail2_kernel(const BayesArgs 
 // Workspace per problem (floats): d[64] e[64] tau[64] (tau[63] = valid flag) mean[LD] reflectors[nref].
 constexpr int GRAM_PITCH = 64;
 template <int QD> __host__ __device__ constexpr int gram_trail_off(int LD) { return 3 * GRAM_PITCH + LD + ((((QD - 1) * QD / 2) + 3) & ~3); }
-template <int QD> __host__ __device__ constexpr int gram_ws_stride(int LD) { return gram_trail_off<QD>(LD) + SPLIT_NR3 * SPLIT_NR3; }
+template <int QD> __host__ __device__ constexpr int gram_full_off(int LD) { return gram_trail_off<QD>(LD) + SPLIT_NR3 * SPLIT_NR3; }   // the whole QD x QD Gram matrix (HANDOFF)
+template <int QD> __host__ __device__ constexpr int gram_ws_stride(int LD) { return gram_full_off<QD>(LD) + QD * QD; }
 
-template <bool FUSED, int QD>
+// HANDOFF: the kernel stops after the Gram matrix and hands it (reversed order, row pitch QD) to tridiag_tail2_kernel
+// through the workspace: the elimination 60 -> 32 then runs with two rows per thread, one warp per problem.
+template <bool FUSED, int QD, bool HANDOFF>
 __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) {
     constexpr int NT = 64, LDQ = (QD + 3) & ~3, NCH = LDQ / 4;
     static_assert(QD <= 64 && QD % 4 == 0, "gram_tridiag_kernel: one row per thread of 2 warps");
@@ -1094,6 +1097,28 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
         }
     }
     __syncthreads();
+    if constexpr (HANDOFF) {
+        static_assert(LDQ == QD, "HANDOFF: QD a multiple of 4");
+        float4 *o = reinterpret_cast<float4 *>(wsp + gram_full_off<QD>(100));
+        const float4 *A4 = reinterpret_cast<const float4 *>(Yt);
+        for (int idx = threadIdx.x; idx < QD * QD / 4; idx += NT) o[idx] = A4[idx];
+        if (a.dbg_mat) {                                 // parity hook: the Gram matrix in natural (un-reversed) patch order
+            float *od = a.dbg_mat + (size_t)blockIdx.x * QD * QD;
+            for (int idx = threadIdx.x; idx < QD * QD; idx += NT) {
+                const int i = idx / QD, j = idx - i * QD;
+                od[idx] = Yt[(QD - 1 - i) * LDQ + (QD - 1 - j)];
+            }
+        }
+        if (a.rank_var) {                                // rank_var = mean over channels of trace(G) (bayes_est.py:39-40)
+            float tr = warp_sum(tid < QD ? Yt[tid * LDQ + tid] : 0.f);
+            __syncthreads();                             // (Yt is read above; red lives behind pb)
+            float *red = (float *)(pb + ((n + 3) & ~3));
+            if (lane == 0) red[warp] = tr;
+            __syncthreads();
+            if (tid == 0) atomicAdd(&a.rank_var[g], (red[0] + red[1]) / (float)C);
+        }
+        return;
+    }
     float2 b[2 * NCH];
     float dg;
     {
@@ -2032,7 +2057,7 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         int ybody = a.L.p * QD > QD * QD ? a.L.p * QD : QD * QD;
         if (ybody < scr) ybody = scr;
         const size_t smem1 = (size_t)(ybody + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
-        auto k1 = gram_tridiag_kernel<FUSED, QD>;
+        auto k1 = g_tail2 ? gram_tridiag_kernel<FUSED, QD, true> : gram_tridiag_kernel<FUSED, QD, false>;
         auto k1c = tridiag_tail_kernel<QD, SPLIT_NR3, 2, 32, 16, GRAM_PITCH, 3 * GRAM_PITCH + 100, gram_trail_off<QD>(100), 0>;
         const size_t smem1c = (size_t)tridiag_scratch_floats<QD, SPLIT_NR3, 2>() * sizeof(float);
         auto k2 = bayes_kernel<FUSED, true, true>;
@@ -2040,9 +2065,13 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
         k1<<<B * p->c, 64, smem1, st>>>(a);
+        if (g_tail2) {      // elimination 60 -> 32 with two rows per thread, one warp per problem
+            auto k1b2 = tridiag_tail2_kernel<QD, QD, 10, GRAM_PITCH, 3 * GRAM_PITCH + 100, gram_full_off<QD>(100), gram_trail_off<QD>(100)>;
+            k1b2<<<B * p->c, 32, (size_t)tridiag2_scratch_floats<QD, QD, SPLIT_NR3>() * sizeof(float), st>>>(a);
+        }
         k1c<<<B * p->c, 32, smem1c, st>>>(a);
         k2<<<FUSED ? B : B * p->c, TT, smem, st>>>(a);
-        return check_launch(what, 3);
+        return check_launch(what, g_tail2 ? 4 : 3);
     }
     if (split) {
         a.L = tri_layout(a.L.n, a.L.p, true);            // no covariance matrix in the eigen/filter kernel

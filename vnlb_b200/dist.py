@@ -72,14 +72,43 @@ def halo_rows(params, max_flow=0.0):
     return halo
 
 
-def make_layout(h, ps, world_size, halo, row_weights=None):
-    """bands[r] = (y0, y1) reference rows owned by rank r, tiles[r] = (ya, yb) rows rank r holds; global rows."""
+def make_layout(h, ps, world_size, halo, row_weights=None, margin=0):
+    """bands[r] = (y0, y1) reference rows owned by rank r, tiles[r] = (ya, yb) rows rank r holds; global rows.
+    `margin` extra rows on each side of a tile let the band borders move by up to `margin` rows during a step
+    (rebalance_bands) without any image data moving."""
     if row_weights is None:
         bands = [partition_rows(h, ps, world_size, r) for r in range(world_size)]
     else:
         bands = [partition_rows_weighted(row_weights, ps, world_size, r) for r in range(world_size)]
-    tiles = [(max(0, a - halo), min(h, b + halo)) for a, b in bands]
+    tiles = [(max(0, a - halo - margin), min(h, b + halo + margin)) for a, b in bands]
     return bands, tiles
+
+
+def rebalanced_cuts(remaining_rows, speeds, bands, bands0, margin, ps):
+    """New band borders from a progress report (host arithmetic, identical on every rank).
+    remaining_rows [H]: reference pixels still masked per global row; speeds[r]: reference pixels rank r cleared per
+    millisecond so far; bands: the current bands (who owns a row now); bands0: the bands the tiles were laid out for.
+    A row's remaining time is its count over its owner's speed; the new borders cut the cumulated time into equal
+    parts, each border kept within `margin` rows of bands0's border (the image rows a tile holds) and the bands kept
+    at least `ps` rows high.  Returns the list of new bands."""
+    rem = np.asarray(remaining_rows, np.float64)
+    h = rem.shape[0]
+    world = len(bands)
+    tau = np.zeros(h)
+    for r, (a, b) in enumerate(bands):
+        tau[a:b] = rem[a:b] / max(float(speeds[r]), 1e-9)
+    cum = np.cumsum(tau)
+    total = float(cum[-1])
+    cuts = [0]
+    for k in range(1, world):
+        orig = bands0[k][0]
+        b = int(np.searchsorted(cum, total * k / world)) + 1 if total > 0 else orig
+        b = min(max(b, orig - margin), orig + margin)
+        cuts.append(max(b, cuts[-1] + ps))
+    cuts.append(h)
+    for k in range(world - 1, 0, -1):                      # keep the last bands non-empty too
+        cuts[k] = min(cuts[k], cuts[k + 1] - ps)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
 def _overlap(a, b):
@@ -166,6 +195,76 @@ def gather_bands(img_tile, ya, bands, rank, h, group=None):
     return full
 
 
+class BandRebalancer:
+    """Mid-step load balancing (the hook of schedule._rounds_async): after the first rounds of a step every rank
+    reports how many reference pixels it has cleared per millisecond and how many are left in each row of its band
+    (one small all-reduce); the band borders move (rebalanced_cuts, at most `margin` rows: the tiles hold those rows
+    already) so that all ranks are predicted to finish together, and the neighbours hand over the mask rows of the
+    moved strips in their CURRENT state.  The number of groups a band produces depends on its content (how widely
+    the similar patches of a region spread), which is unknown before the step has run for a while."""
+
+    def __init__(self, bands, tiles, rank, group, margin, h, w, t, ps, pt, proc_step):
+        self.bands0 = list(bands)                # borders may move within +-margin of THESE
+        self.bands = list(bands)
+        self.tiles, self.rank, self.group, self.margin = tiles, rank, group, margin
+        self.h, self.ps = h, ps
+        self.lattice_per_row = (t - pt + 1) * (w - ps + 1) / float(proc_step ** 2)
+        self.t0 = None
+        self.moved = []
+
+    def start(self):
+        self.t0 = torch.cuda.Event(enable_timing=True)
+        self.t0.record()
+
+    def __call__(self, mask):
+        world, rank, h = len(self.bands), self.rank, self.h
+        (y0, y1), ya = self.bands[rank], self.tiles[rank][0]
+        rem = mask.sum(dim=(0, 2), dtype=torch.float32)                       # remaining reference pixels per tile row
+        now = torch.cuda.Event(enable_timing=True)
+        now.record()
+        now.synchronize()
+        elapsed = max(self.t0.elapsed_time(now), 1e-3)
+        vec = torch.zeros((h + 2 * world,), dtype=torch.float32, device=mask.device)
+        vec[y0:y1] = rem[y0 - ya:y1 - ya]
+        initial = self.lattice_per_row * max(min(y1, h - self.ps + 1) - y0, 0)
+        vec[h + rank] = elapsed
+        vec[h + world + rank] = initial
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=self.group)
+        v = vec.cpu().numpy().astype(np.float64)
+        rem_rows, el, ini = v[:h], v[h:h + world], v[h + world:]
+        speeds = [max(ini[r] - rem_rows[a:b].sum(), 1.0) / max(el[r], 1e-3) for r, (a, b) in enumerate(self.bands)]
+        new = rebalanced_cuts(rem_rows, speeds, self.bands, self.bands0, self.margin, self.ps)
+        self._migrate(mask, new)
+        self.moved.append(dict(old=self.bands[rank], new=new[rank], elapsed_ms=[round(float(x), 2) for x in el],
+                               speeds=[round(float(x), 1) for x in speeds]))
+        self.bands = new
+
+    def _migrate(self, mask, new):
+        """Mask rows of the strips that change owner go from the old owner to the new one (current state)."""
+        rank, ya = self.rank, self.tiles[self.rank][0]
+        sends, recvs, put = [], [], []
+        for r in range(len(new)):
+            if r == rank:
+                continue
+            lost = _overlap(self.bands[rank], new[r])            # rows I owned that r owns now
+            gain = _overlap(self.bands[r], new[rank])            # rows r owned that I own now
+            if lost:
+                lo, hi = lost
+                sends.append((mask[:, lo - ya:hi - ya].contiguous(), r))
+            if gain:
+                lo, hi = gain
+                buf = torch.empty((mask.shape[0], hi - lo, mask.shape[2]), dtype=mask.dtype, device=mask.device)
+                recvs.append((buf, r))
+                put.append((lo, hi, buf))
+        _p2p(sends, recvs, self.group)
+        for r in range(len(new)):
+            lost = _overlap(self.bands[rank], new[r]) if r != rank else None
+            if lost:
+                mask[:, lost[0] - ya:lost[1] - ya] = 0
+        for lo, hi, buf in put:
+            mask[:, lo - ya:hi - ya] = buf
+
+
 # ------------------------------------------------------------------------------------------------ inputs
 def _rows_to_device(x, ya, yb, device):
     """Rows [ya, yb) of a [T,C,H,W] host (numpy / torch, ideally pinned) or device array as a contiguous float32 device
@@ -198,14 +297,19 @@ def _max_flow_y(flows, y0, y1):
 
 
 def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="default", params=None, stats=None,
-                        group=None, device=None, clean=None, max_flow=None, row_weights=None, gather=True):
+                        group=None, device=None, clean=None, max_flow=None, row_weights=None, gather=True,
+                        rebalance=True, rebalance_round=2, margin_frac=0.10):
     """vnlb.denoise over all ranks of `group`.  Every rank passes the same `noisy` [T,C,H,W] (host, ideally pinned, or
     device) and the same `flows`; only its own band + halo rows are copied to its GPU.  Returns (deno, basic, seconds):
-    the full frames on every rank (gather=True) or this rank's band rows only as (deno_band, basic_band, (y0, y1)).
+    the full frames on every rank (gather=True) or, with gather=False, this rank's band rows only as
+    (deno_band, basic_band, ((y0, y1) of deno_band, (y0, y1) of basic_band)) -- the estimate stays sharded like the work.
 
     max_flow : bound on |flow_y| in pixels per frame used to size the halo; None = measured on this rank's band rows
                (a host pass over them) and agreed over the ranks (max).  The bound is verified on the device.
-    row_weights : optional [H] expected cost per reference row for the band partition (None = equal row counts).
+    row_weights : optional [H] expected cost per reference row for the initial band partition (None = equal row counts).
+    rebalance : move the band borders once per step, after `rebalance_round` rounds, to equalise the predicted
+               remaining time of the ranks (BandRebalancer); the tiles carry `margin_frac` x band rows of extra
+               margin on each side for that.
     """
     clock = Timer()
     clock.tic()
@@ -221,7 +325,7 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
     params = params if params is not None else get_params(sigma, False, version)
     ps = int(params["sizePatch"][0])
     with torch.cuda.device(device):
-        # ---- layout: band of reference rows, tile = band + halo
+        # ---- layout: band of reference rows, tile = band + halo (+ margin for the moving borders)
         has_flow = flows is not None and flows.get("fflow") is not None and flows.get("bflow") is not None
         if has_flow and max_flow is None:
             y0u, y1u = partition_rows(H, ps, world, rank)
@@ -229,9 +333,10 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
             dist.all_reduce(mf, op=dist.ReduceOp.MAX, group=group)
             max_flow = float(mf.item())
         halo = halo_rows(params, max_flow if has_flow else 0.0)
-        bands, tiles = make_layout(H, ps, world, halo, row_weights)
-        (y0, y1), (ya, yb) = bands[rank], tiles[rank]
-        give, take = exchange_plan(bands, tiles, rank)
+        rebalance = bool(rebalance) and world > 1
+        margin = int(math.ceil(margin_frac * (H / world))) if rebalance else 0
+        bands, tiles = make_layout(H, ps, world, halo, row_weights, margin)
+        ya, yb = tiles[rank]
         # ---- inputs: only the tile's rows are copied to this GPU
         noisy_t = _rows_to_device(noisy, ya, yb, device)
         dflows = AttrDict(fflow=None, bflow=None)
@@ -244,8 +349,16 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
             flow_ok = torch.maximum(ff[:, 1].abs().amax(), bf[:, 1].abs().amax()) <= max_flow + 1e-6
         sent = [0, 0]
         st = stats if stats is not None else {}
+        reb = None
+        if rebalance:
+            reb = BandRebalancer(bands, tiles, rank, group, margin, H, W, T, ps, int(params["sizePatchTime"][0]),
+                                 int(params["procStep"][0]))
+        cur = dict(bands=bands)
 
         def reduce_fn(images):
+            if reb is not None:
+                cur["bands"] = reb.bands                   # the borders as they are at the end of the step
+            give, take = exchange_plan(cur["bands"], tiles, rank)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if stats is not None else None
             if ev:
                 ev[0].record()
@@ -255,32 +368,49 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
                 stats.setdefault("exchange_events", []).append(ev)
 
         def post_fn(images):
+            give, take = exchange_plan(cur["bands"], tiles, rank)
             sent[1] += exchange_halo(images.deno, ya, give, take, group)
 
         noisy_yuv = color.rgb2yuv(noisy_t)
         tile = (ya, H)
-        band_local = (y0 - ya, y1 - ya)
-        images = alloc.allocate_images_lean(noisy_yuv, None, None)
-        proc_nl_fast(images, dflows, get_args(params, C, 0, device), st, band_local, reduce_fn, tile, post_fn)
-        basic_t, basic_yuv = images.deno, images.deno_yuv
-        images = alloc.allocate_images_lean(noisy_yuv, basic_yuv, None)
-        proc_nl_fast(images, dflows, get_args(params, C, 1, device), st, band_local, reduce_fn, tile, None)
-        deno_t = images.deno
+        side = torch.cuda.Stream(device=device) if gather else None
+        outs = []
+        basic_yuv = None
+        for step in (0, 1):
+            y0, y1 = cur["bands"][rank]
+            images = alloc.allocate_images_lean(noisy_yuv, basic_yuv, None)
+            hook = None
+            if reb is not None:
+                reb.start()
+                hook = (int(rebalance_round), reb)
+            proc_nl_fast(images, dflows, get_args(params, C, step, device), st, (y0 - ya, y1 - ya), reduce_fn, tile,
+                         post_fn if step == 0 else None, hook)
+            band_s = list(cur["bands"])
+            if step == 0:
+                basic_yuv = images.deno_yuv
+            if gather and step == 0:                       # the basic bands travel while step 2 computes
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    outs.append(gather_bands(images.deno, ya, band_s, rank, H, group))
+            elif gather:
+                outs.append(gather_bands(images.deno, ya, band_s, rank, H, group))
+            else:
+                b0, b1 = band_s[rank]
+                outs.append((images.deno[:, :, b0 - ya:b1 - ya].contiguous(), (b0, b1)))
         if gather:
-            deno = gather_bands(deno_t, ya, bands, rank, H, group)
-            basic = gather_bands(basic_t, ya, bands, rank, H, group)
-        else:
-            deno = deno_t[:, :, y0 - ya:y1 - ya].contiguous()
-            basic = basic_t[:, :, y0 - ya:y1 - ya].contiguous()
+            torch.cuda.current_stream().wait_stream(side)
+            outs[0].record_stream(torch.cuda.current_stream())     # allocated on the side stream, used by the caller on this one
         torch.cuda.synchronize(device)
         if flow_ok is not None and not bool(flow_ok):
             raise ValueError("denoise_distributed: |flow_y| exceeds max_flow = %g on rank %d; the halo (%d rows) is too small"
                              % (max_flow, rank, halo))
         if stats is not None:
-            stats["layout"] = dict(band=(y0, y1), tile=(ya, yb), halo=halo, rows_copied=yb - ya, rows_total=H)
+            stats["layout"] = dict(band=bands[rank], tile=(ya, yb), halo=halo, margin=margin, rows_copied=yb - ya, rows_total=H)
             stats["exchange_bytes"] = dict(accumulators=sent[0], halo=sent[1])
+            if reb is not None:
+                stats["rebalance"] = reb.moved
             if "exchange_events" in stats:
                 stats["exchange_ms"] = [a.elapsed_time(b) for a, b in stats.pop("exchange_events")]
     if gather:
-        return deno, basic, clock.toc()
-    return deno, basic, (y0, y1)
+        return outs[1], outs[0], clock.toc()
+    return outs[1][0], outs[0][0], (outs[1][1], outs[0][1])

@@ -21,6 +21,11 @@ def denoise(noisy, sigma, gpuid=0, clean=None, verbose=True, flows=None, schedul
             'fflow'/'bflow' of shape [T,2,H,W] or [T-1,2,H,W] (channel 0 = dx, 1 = dy)
     schedule : "fast" (device-side rounds) or "parity" (the reference's exact
             sub-batch schedule and th.randperm draws)
+    version  : parameter table, see params.get_params.  The default is the classic VNLB table (`default_params`,
+            what BASELINE.json names); the reference's own get_params hard-codes "iphone" (15x15 window, +-10
+            frames, needle search), so `vnlb.denoise(noisy, sigma)` corresponds to version="iphone" here (served
+            with the l2 search).  The similarity search follows the restated semantics documented in README.md
+            (window_mode, dist_chnls): the reference's search lives in the absent vpss package.
     returns (deno, basic, seconds): float32 CUDA tensors [T,C,H,W] and the wall time
             of the call including the host->device copy, after a device sync.
     """

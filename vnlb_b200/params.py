@@ -34,7 +34,10 @@ def default_params(sigma, verbose=False):
 
 
 def get_params(sigma, verbose=False, version="default"):
-    """lib/vnlb/params.py:52-100 with the version as an argument."""
+    """lib/vnlb/params.py:52-100 with the version as an argument.  NOTE the default: the classic VNLB table of
+    `default_params` (27x27 window, +-6 frames, 7x7x2 patches -- the values BASELINE.json names), whereas the
+    reference's get_params is hard-coded to version = "iphone" (15x15 window, +-10 frames, pt = [1, 2], "needle" search
+    in step 1).  Pass version="iphone" for that table (with the l2 search, and a warning)."""
     params = default_params(sigma, verbose)
     if version in ("default", "exp"):
         pass
@@ -47,6 +50,9 @@ def get_params(sigma, verbose=False, version="default"):
         if version == "iphone":
             # the reference pairs this with stype "needle" in step 1 (params.py:88), a
             # vpss search variant outside this path; the l2 search is used instead
+            import warnings
+            warnings.warn("vnlb_b200.get_params(version='iphone'): the reference's step-1 'needle' search (vpss) is not part of "
+                          "this path; the l2 search is used for both steps", stacklevel=2)
             params["stype"] = ["l2", "l2"]
     else:
         raise ValueError("unknown params version [%s]" % version)

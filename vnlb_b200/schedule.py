@@ -75,14 +75,16 @@ class _Workspace:
         return ws
 
 
-def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed, est_mask, row_hist=None):
+def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed, est_mask, row_hist=None, sync_hook=None):
     """The rounds of one step on two streams: [count, draw, search, clear mask] of round r+1 runs on the search
     stream while the fused Bayes kernels of round r run on the Bayes stream (the mask only depends on the search
     results, never on the filtered patches).  The host never waits for the GPU inside the loop: every kernel of a
     round is enqueued with `cap` rows (rows beyond the number actually drawn are padded to invalid queries
     and skipped on the device), the round size is read back two rounds late from a ring of pinned counters,
     and the draw probability is computed from that (stale, hence conservative) count.  The loop ends when a
-    read-back says the mask is empty; the one or two extra rounds already enqueued are no-ops."""
+    read-back says the mask is empty; the one or two extra rounds already enqueued are no-ops.
+    `sync_hook` = (round index R, fn): multi-GPU load balancing -- before round R is enqueued (or after the loop, if it
+    ends earlier) the streams are drained and fn(mask) runs exactly once; it may rewrite rows of the mask."""
     t, c, h, w = images.shape
     main = torch.cuda.current_stream()
     sA, sB = ws.search_stream, ws.bayes_stream
@@ -101,7 +103,15 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
     tm = L.timer
     rows_of = [cap] * 4
     r = 0
+    hook_done = sync_hook is None
     while True:
+        if not hook_done and r == sync_hook[0]:
+            hook_done = True
+            sA.synchronize()
+            sB.synchronize()
+            with torch.cuda.stream(sA):
+                sync_hook[1](mask)
+                remaining = max(int(mask.sum().item()), 1)
         buf, slot = r & 1, r & 3
         target = min(cap, max(qmin, int(remaining * frac)))
         prob = 1.0 if remaining <= target else target / remaining * 0.97
@@ -160,13 +170,25 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
     last = (r - 1) & 3
     copied[last].synchronize()
     nproc += min(int(ws.host4[last][1]), rows_of[last])
+    if not hook_done:                    # the step ended before round R: still take part in the collective, then finish
+        sA.synchronize()
+        sB.synchronize()
+        with torch.cuda.stream(sA):
+            sync_hook[1](mask)
+            left = int(mask.sum().item())
+        if left > 0:                     # rows received from a neighbour: process them with the plain loop
+            ndrop1 = int(ws.dropped.item()) if dedup else 0
+            main.wait_stream(sA)
+            main.wait_stream(sB)
+            n2, r2, _, d2 = _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed + 1, left, row_hist, None)
+            return nproc - ndrop1 + n2, nrounds + r2, nmask0, ndrop1 + d2
     main.wait_stream(sA)
     main.wait_stream(sB)
     ndrop = int(ws.dropped.item()) if dedup else 0          # (end of the step: the one host sync of the loop)
     return nproc - ndrop, nrounds, nmask0, ndrop
 
 
-def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None, tile=None, post_fn=None):
+def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None, tile=None, post_fn=None, sync_hook=None):
     """One VNLB step with the throughput schedule (same contract as proc_nl).  `y_range` / `tile`: multi-GPU band of
     reference rows and position of this row tile in the frame (mask.init_mask_device)."""
     dev = images.device
@@ -196,7 +218,7 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None, 
             row_hist = torch.zeros((h,), dtype=torch.float32, device=dev)
             stats["row_hist"] = row_hist
         nproc, nrounds, nmask0, ndrop = _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed,
-                                                      est + est // 8, row_hist)
+                                                      est + est // 8, row_hist, sync_hook)
         finish_step(images, args, reduce_fn, post_fn)
         if stats is not None:
             stats.setdefault("ndropped", []).append(ndrop)
