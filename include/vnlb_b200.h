@@ -109,6 +109,13 @@ int vnlb_init_mask_tile(int8_t *mask, int T, int H, int W, int ps, int pt, int p
  * vals float32 [Q,k], inds int64 [Q,k] written in place, ascending by
  * (distance, candidate enumeration order t->y->x); slots that cannot be filled
  * (fewer than k candidates) are set to +inf / -1. */
+/* Search kernel selection (A/B measurements and tests; every path returns identical bits): 0 = automatic -- for
+ * 7x7x2 patches, a 27x27 window and at most 13 frames the "quad" kernel (4x9 candidates per thread, accumulators in
+ * registers over all channel / patch-frame phases), its frame tiles staged by TMA (cp.async.bulk.tensor.3d) when
+ * W % 4 == 0 and the image is 16-byte aligned, by 4-byte cp.async otherwise; 1 = never the quad kernel (1-column tiled
+ * kernel / generic kernel); 2 = quad kernel without TMA.  Returns the previous setting.
+ * (Environment: VNLB_SEARCH_PATH at start-up.) */
+int vnlb_set_search_path(int path);
 size_t vnlb_search_workspace_bytes(int Q, const VnlbSearchParams *p);
 int vnlb_search_topk(const float *img, int T, int C, int H, int W, const int64_t *qinds, int Q,
                      const float *fflow, const float *bflow, const VnlbSearchParams *p,

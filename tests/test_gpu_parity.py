@@ -180,6 +180,46 @@ def test_search_with_flows_bit_exact(vb):
         np.testing.assert_array_equal(gv, ov)
 
 
+QUAD_SHAPES = [
+    # (T, H, W, nWt, window_mode, flows): TMA staging (W % 4 == 0, frame >= one 36 x 33 box) and cp.async staging,
+    # windows that hang over the frame border (zero-filled by TMA), frames narrower than the window, fewer frames than
+    # the temporal range, clipped windows, flow trajectories (one tile per frame and patch frame)
+    (16, 72, 88, 6, "shift", False), (16, 72, 88, 6, "shift", True), (9, 56, 70, 4, "shift", True),
+    (15, 40, 48, 6, "clip", True), (4, 33, 36, 6, "shift", False), (5, 30, 31, 2, "clip", False),
+    (14, 64, 50, 6, "shift", True), (3, 21, 64, 6, "shift", False),
+]
+
+
+@pytest.mark.parametrize("T,H,W,nwt,mode,with_flows", QUAD_SHAPES)
+def test_search_kernel_variants_return_identical_bits(vb, T, H, W, nwt, mode, with_flows):
+    """The quad kernel (4 x 9 candidates per thread; TMA or cp.async staging) against the 1-column tiled kernel and
+    the CPU oracle: indices and distances bit-identical, steps 1 and 2 (vnlb_set_search_path: 0 auto, 1 tiled, 2 quad
+    without TMA)."""
+    from vnlb_b200 import _lib as L
+    rs = np.random.RandomState(T * 1000 + W)
+    img = (rs.rand(T, 3, H, W) * 255).astype(np.float32)
+    flows = None
+    if with_flows:
+        flows = dict(fflow=((rs.rand(T, 2, H, W) - 0.5) * 7).astype(np.float32),
+                     bflow=((rs.rand(T, 2, H, W) - 0.5) * 7).astype(np.float32))
+    q = rand_queries(rs, T, H, W, 7, 2, 40)
+    prev = L.lib.vnlb_set_search_path(0)
+    try:
+        for step in (0, 1):
+            over = dict(sizeSearchTimeFwd=nwt, sizeSearchTimeBwd=nwt, nSimilarPatches=60)
+            a_gpu = gargs(vb, step, window_mode=mode, **over)
+            ov = np.full((q.shape[0] + 3, 60), np.inf, np.float32)
+            oi = np.full((q.shape[0] + 3, 60), -1, np.int64)
+            orc.exec_sim_search_burst(img, q, ov, oi, flows, 20., oargs(step, **over), window_mode=mode)
+            for path in (0, 1, 2):
+                L.lib.vnlb_set_search_path(path)
+                gv, gi = run_search(vb, img, q, a_gpu, flows)
+                np.testing.assert_array_equal(gi, oi, err_msg="path %d step %d" % (path, step))
+                np.testing.assert_array_equal(gv, ov, err_msg="path %d step %d" % (path, step))
+    finally:
+        L.lib.vnlb_set_search_path(prev)
+
+
 def test_search_exact_ties_follow_enumeration_order(vb):
     """Constant image: every distance is 0; the documented tie-break (enumeration
     order frame -> y -> x) must be reproduced exactly."""

@@ -35,7 +35,7 @@ class BayesParams(ctypes.Structure):
 EXPORTS = [
     "vnlb_kernel_launches",
     "vnlb_last_error", "vnlb_version", "vnlb_rgb2yuv", "vnlb_yuv2rgb", "vnlb_init_mask", "vnlb_init_mask_tile",
-    "vnlb_search_workspace_bytes", "vnlb_search_topk", "vnlb_fill_patches", "vnlb_mask_update",
+    "vnlb_set_search_path", "vnlb_search_workspace_bytes", "vnlb_search_topk", "vnlb_fill_patches", "vnlb_mask_update",
     "vnlb_count_mask", "vnlb_select_queries", "vnlb_pad_queries", "vnlb_round_dedup",
     "vnlb_flat_areas", "vnlb_bayes_workspace_bytes", "vnlb_bayes_filter", "vnlb_bayes_debug", "vnlb_bayes_matrix_dim", "vnlb_bayes_fused_supported", "vnlb_set_bayes_split", "vnlb_bayes_aggregate_fused", "vnlb_aggregate",
     "vnlb_normalize",
@@ -59,6 +59,7 @@ lib.vnlb_rgb2yuv.argtypes = [_vp, _vp, _i, _i, _i, _i, _vp]
 lib.vnlb_yuv2rgb.argtypes = [_vp, _vp, _i, _i, _i, _i, _vp]
 lib.vnlb_init_mask.argtypes = [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
 lib.vnlb_init_mask_tile.argtypes = [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]
+lib.vnlb_set_search_path.argtypes = [_i]
 lib.vnlb_search_workspace_bytes.argtypes = [_i, ctypes.POINTER(SearchParams)]
 lib.vnlb_search_topk.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, ctypes.POINTER(SearchParams),
                                  _vp, _vp, _vp, _sz, _vp]

@@ -16,6 +16,10 @@
 //                column of 9 candidates, the query patch lives in registers.
 // Selection: 4-pass radix select on the distance bits in shared memory, tie
 // resolution by enumeration order, bitonic sort of the k survivors.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace vnlb {
@@ -37,10 +41,12 @@ struct alignas(16) SearchShared {
     unsigned int sel_neq;
     int sel_last;
     int sel_count;
-    unsigned int red_min[8];
-    unsigned int red_max[8];
+    unsigned int red_min[16];
+    unsigned int red_max[16];
+    unsigned int hist2[256];  // quad kernel: second (linear) histogram of the register-resident selection
     int sel_bin;
     unsigned int sel_less;
+    int shared_win;   // quad kernel: every frame has the same window and the frames are consecutive
 };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -117,6 +123,78 @@ __device__ void build_windows(SearchShared &S, int t0, int y0, int x0, int T, in
     S.ncand = off;
 }
 
+// Warp 0 of the quad kernel (at most 32 frames): lane 0 follows the forward flow, lane 1 the backward flow (two
+// independent chains of dependent loads), then lane f computes the window of frame f and a warp scan gives the
+// candidate offsets.  Same results as build_windows; also sets S.shared_win.
+__device__ void build_windows_warp(SearchShared &S, int t0, int y0, int x0, int T, int H, int W,
+                                   const float *__restrict__ fflow, const float *__restrict__ bflow,
+                                   const VnlbSearchParams &p) {
+    const int lane = threadIdx.x & 31;
+    int r0, r1;
+    if (p.window_mode == VNLB_WINDOW_SHIFT) {
+        const int shift = min(0, t0 - p.nWt_b) + max(0, t0 + p.nWt_f - T + p.pt);
+        r0 = max(0, t0 - p.nWt_b - shift);
+        r1 = min(T - p.pt, t0 + p.nWt_f - shift);
+    } else {
+        r0 = max(0, t0 - p.nWt_b);
+        r1 = min(T - p.pt, t0 + p.nWt_f);
+    }
+    const int nfr = r1 - r0 + 1;
+    const long long HW = (long long)H * W;
+    if (lane == 0) {
+        int px = x0, py = y0;
+        S.fw[t0 - r0].x0 = px;
+        S.fw[t0 - r0].y0 = py;
+        for (int qt = t0 + 1; qt <= r1; ++qt) {
+            if (fflow) {
+                const float dx = fflow[((long long)(qt - 1) * 2 + 0) * HW + (long long)py * W + px];
+                const float dy = fflow[((long long)(qt - 1) * 2 + 1) * HW + (long long)py * W + px];
+                px = clampi((int)roundf((float)px + dx), 0, W - 1);
+                py = clampi((int)roundf((float)py + dy), 0, H - 1);
+            }
+            S.fw[qt - r0].x0 = px;
+            S.fw[qt - r0].y0 = py;
+        }
+    } else if (lane == 1) {
+        int px = x0, py = y0;
+        for (int qt = t0 - 1; qt >= r0; --qt) {
+            if (bflow) {
+                const float dx = bflow[((long long)(qt + 1) * 2 + 0) * HW + (long long)py * W + px];
+                const float dy = bflow[((long long)(qt + 1) * 2 + 1) * HW + (long long)py * W + px];
+                px = clampi((int)roundf((float)px + dx), 0, W - 1);
+                py = clampi((int)roundf((float)py + dy), 0, H - 1);
+            }
+            S.fw[qt - r0].x0 = px;
+            S.fw[qt - r0].y0 = py;
+        }
+    }
+    __syncwarp();
+    int ax = 0, nx = 0, ay = 0, ny = 0;
+    if (lane < nfr) {
+        spatial_range(S.fw[lane].x0, W, p.ps, p.w_s, p.window_mode, ax, nx);
+        spatial_range(S.fw[lane].y0, H, p.ps, p.w_s, p.window_mode, ay, ny);
+    }
+    const int cnt = lane < nfr ? nx * ny : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    __syncwarp();
+    if (lane < nfr) {
+        FrameWin w;
+        w.t = r0 + lane; w.x0 = ax; w.y0 = ay; w.nx = nx; w.ny = ny; w.off = incl - cnt;
+        S.fw[lane] = w;
+    }
+    const int ax0 = __shfl_sync(0xffffffffu, ax, 0), ay0 = __shfl_sync(0xffffffffu, ay, 0);
+    const int nx0 = __shfl_sync(0xffffffffu, nx, 0), ny0 = __shfl_sync(0xffffffffu, ny, 0);
+    const bool same = lane >= nfr || (ax == ax0 && ay == ay0 && nx == nx0 && ny == ny0);
+    const bool sw = __all_sync(0xffffffffu, same);
+    if (lane == nfr - 1) S.ncand = incl;
+    if (lane == 0) { S.nfr = nfr; S.shared_win = sw ? 1 : 0; }
+}
+
 // candidate enumeration order -> (frame slot, qy, qx)
 __device__ __forceinline__ void cand_coords(const SearchShared &S, int cand, int &f, int &qy, int &qx) {
     f = 0;
@@ -141,6 +219,7 @@ __device__ __forceinline__ void cand_coords(const SearchShared &S, int cand, int
 // with ballot-scan tie resolution takes over.  Both give the same answer.
 // ---------------------------------------------------------------------------
 constexpr int kKeyCap = 512;
+constexpr int kRankCap = 160;   // quad kernel: survivors ranked by counting instead of sorted
 
 __device__ void bitonic_sort_keys(unsigned long long *keys, int P) {
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -158,6 +237,24 @@ __device__ void bitonic_sort_keys(unsigned long long *keys, int P) {
             }
             __syncthreads();
         }
+}
+
+// rows of the output: the m smallest keys (sorted) as (distance, index); the rest of the k slots invalid
+__device__ void write_topk(const SearchShared &S, const unsigned long long *keys, int m, int k, float *__restrict__ out_vals,
+                           long long *__restrict__ out_inds, int C, int H, int W) {
+    const long long CHW = (long long)C * H * W;
+    for (int r = threadIdx.x; r < k; r += blockDim.x) {
+        if (r < m) {
+            const unsigned long long key = keys[r];
+            int f, qy, qx;
+            cand_coords(S, (int)(key & 0xffffffffu), f, qy, qx);
+            out_vals[r] = __uint_as_float((unsigned)(key >> 32));
+            out_inds[r] = (long long)S.fw[f].t * CHW + (long long)qy * W + qx;
+        } else {
+            out_vals[r] = __int_as_float(0x7f800000);
+            out_inds[r] = -1;
+        }
+    }
 }
 
 __device__ void select_topk(SearchShared &S, const float *dist, unsigned long long *keys, int k, unsigned int tmin,
@@ -292,19 +389,7 @@ __device__ void select_topk(SearchShared &S, const float *dist, unsigned long lo
         }
         bitonic_sort_keys(keys, P);
     }
-    const long long CHW = (long long)C * H * W;
-    for (int r = tid; r < k; r += nthr) {
-        if (r < m) {
-            const unsigned long long key = keys[r];
-            int f, qy, qx;
-            cand_coords(S, (int)(key & 0xffffffffu), f, qy, qx);
-            out_vals[r] = __uint_as_float((unsigned)(key >> 32));
-            out_inds[r] = (long long)S.fw[f].t * CHW + (long long)qy * W + qx;
-        } else {
-            out_vals[r] = __int_as_float(0x7f800000);
-            out_inds[r] = -1;
-        }
-    }
+    write_topk(S, keys, m, k, out_vals, out_inds, C, H, W);
 }
 
 // ---------------------------------------------------------------------------
@@ -524,6 +609,425 @@ search_tiled_kernel(const float *__restrict__ img, int T, int C, int H, int W,
     select_topk(S, dist, keys, p.k, tmin, tmax, ov, oi, C, H, W);
 }
 
+// ---------------------------------------------------------------------------
+// quad kernel: ps = 7, pt = 2, w_s = 27, at most 13 frames in the temporal window (the production shape).
+//
+// Work item = (frame f, strip s of 9 candidate rows, quad j of 4 candidate columns): 21 items per frame, all frames of
+// the temporal window at once -> 273 of 288 threads busy for 13 frames (the CTA is launched with 21 * frames threads,
+// rounded up to whole warps).  A thread owns its 36 candidates for the WHOLE query: the accumulators stay in registers
+// over the (channel, patch frame) phases, so the distances never round-trip through shared memory between phases and
+// the per-candidate accumulation order is exactly the canonical (c, ht, hy, hx) one.  Per phase the thread keeps the
+// 49-value query plane in registers (13 broadcast LDS.128) and slides down 15 tile rows with 2 LDS.128 + 1 LDS.64 each,
+// feeding 4 x 9 accumulators: 58 shared-memory loads per 3528 FSUB/FFMA (the 1-column kernel above: 154 per 882).
+// Tiles are 36 x 33 boxes (row pitch 36 floats, 16-byte aligned quads), one per frame, ALL frames of a phase resident:
+//   * TMA path (W % 4 == 0): one elected thread issues one cp.async.bulk.tensor.3d per frame on the [T*C, H, W]
+//     tensor map of the search image (box start = window corner, any alignment; out-of-frame columns/rows are
+//     zero-filled and only ever read by candidates that are discarded), completion on an mbarrier;
+//   * cp.async path (any W): one warp per tile row, 4-byte copies.
+// Zero flow / rigid trajectory (all frames share one window): frames+1 tiles are staged once per channel and serve
+// both patch frames.  The distances are then written to shared memory (aliasing the tiles) and selected as above.
+// ---------------------------------------------------------------------------
+constexpr int QROWS = 9, QCOLS = 4, QQUADS = 7, QSTRIPS = 3;
+constexpr int QITEMS = QQUADS * QSTRIPS;   // 21 items per frame
+constexpr int QTW = 36;                    // tile row pitch (floats) = TMA box width
+constexpr int QTH = TTILE;                 // 33 tile rows
+constexpr int QSLOT = 1204;                // floats per tile slot: 33 * 36 = 1188, padded to 301 x 16 bytes (301 = 5 mod 8: with the
+                                           // frame as the fastest item index, 8 consecutive lanes read 8 different 16-byte bank groups)
+constexpr int QMAXF = 13;                  // frames of the temporal window
+constexpr int QTHREADS = ((QMAXF * QITEMS + 31) / 32) * 32;   // 288
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "QUAD_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra QUAD_DONE;\n"
+        "bra QUAD_WAIT;\n"
+        "QUAD_DONE:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_box(float *dst_smem, const CUtensorMap *map, unsigned long long *bar, int x, int y, int z) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(d),
+        "l"(map), "r"(b), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+// one (channel, patch frame) plane of one item: 36 candidates x 49 terms.  The loop over the patch row hy is NOT
+// unrolled: its body (9 tile rows x 56 FSUB/FFMA pairs + 29 shared-memory loads, 8.5 KB of code) stays in the
+// instruction cache; the fully unrolled plane (56 KB) ran at 54 % issue utilisation with `no_instruction` as its top
+// stall reason (profiles/r2_search_summary.md).  qp: the query plane as [7][8] floats.
+__device__ __forceinline__ void quad_row(const float *__restrict__ row, float (&v)[10]) {
+    const float4 a = *reinterpret_cast<const float4 *>(row);
+    const float4 b = *reinterpret_cast<const float4 *>(row + 4);
+    const float2 e = *reinterpret_cast<const float2 *>(row + 8);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = e.x; v[9] = e.y;
+}
+__device__ __forceinline__ void quad_terms(const float (&q)[7], const float (&v)[10], float *acc4) {
+#pragma unroll
+    for (int hx = 0; hx < TPS; ++hx)
+#pragma unroll
+        for (int col = 0; col < QCOLS; ++col) {
+            const float d = __fsub_rn(q[hx], v[col + hx]);
+            acc4[col] = __fmaf_rn(d, d, acc4[col]);
+        }
+}
+__device__ __forceinline__ void quad_qrow(const float *__restrict__ qp, float (&q)[7]) {
+    const float4 q0 = *reinterpret_cast<const float4 *>(qp);
+    const float4 q1 = *reinterpret_cast<const float4 *>(qp + 4);
+    q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w; q[4] = q1.x; q[5] = q1.y; q[6] = q1.z;
+}
+__device__ __forceinline__ void quad_plane(const float *__restrict__ qp, const float *__restrict__ tp, float (&acc)[QROWS * QCOLS]) {
+    // patch rows in blocks of two: tile row hy + rr serves candidate row rr (patch row hy) and candidate row rr - 1
+    // (patch row hy + 1), so a block loads 10 tile rows instead of 18; each candidate still sees hy ascending
+#pragma unroll 1
+    for (int hy = 0; hy < TPS - 1; hy += 2) {
+        float qa[7], qb[7];
+        quad_qrow(qp + hy * 8, qa);
+        quad_qrow(qp + hy * 8 + 8, qb);
+        const float *row = tp + hy * QTW;
+#pragma unroll
+        for (int rr = 0; rr < QROWS + 1; ++rr) {
+            float v[10];
+            quad_row(row + rr * QTW, v);
+            if (rr > 0) quad_terms(qb, v, &acc[(rr - 1) * QCOLS]);
+            if (rr < QROWS) quad_terms(qa, v, &acc[rr * QCOLS]);
+        }
+    }
+    {
+        float qa[7];
+        quad_qrow(qp + (TPS - 1) * 8, qa);
+        const float *row = tp + (TPS - 1) * QTW;
+#pragma unroll
+        for (int s = 0; s < QROWS; ++s) {
+            float v[10];
+            quad_row(row + s * QTW, v);
+            quad_terms(qa, v, &acc[s * QCOLS]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Selection with the distances in registers (quad kernel): two histograms instead of two sorts.
+//   1. block min / max of the distance bits;
+//   2. histogram of a lattice SAMPLE (two candidates per thread) over 256 bins of the bit pattern (monotone in the
+//      distance, logarithmic resolution): bin b1 below which about 2 m candidates fall;
+//   3. the candidates up to bin b1 (a lower set, a few hundred) are appended to a list in shared memory;
+//   4. histogram of the LIST over 256 bins linear in the distance: bin b2 at which the cumulated count reaches m;
+//      the entries up to b2 (a lower set of m + a few) are bitonic-sorted on (distance bits, enumeration order).
+// Both filters are monotone in the distance, so the sorted set contains every candidate smaller than any excluded
+// one and all of its ties: the result is exactly the reference order.  Too few / too many survivors (heavy ties, tiny
+// windows) fall back to select_topk on the distances written to shared memory.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int warp_find_bin(const unsigned int *hist, unsigned int need, unsigned int &cum_out) {
+    // warp 0: smallest bin whose inclusive cumulated count reaches `need` (255 and the total if it never does)
+    const int lane = threadIdx.x & 31;
+    unsigned int loc[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; sum += loc[j]; }
+    unsigned int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const unsigned int excl = incl - sum;
+    int bin = 255 + 256;                       // "not found" sentinel, larger than any bin
+    unsigned int cum = 0;
+    if (need > excl && need <= incl) {
+        unsigned int run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (need > run && need <= run + loc[j]) { bin = lane * 8 + j; cum = run + loc[j]; }
+            run += loc[j];
+        }
+    }
+    const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int best = __reduce_min_sync(0xffffffffu, bin);
+    const unsigned int bcum = __reduce_max_sync(0xffffffffu, cum);
+    if (best > 255) { cum_out = total; return 255; }
+    cum_out = bcum;
+    return best;
+}
+
+// returns false (block-uniform) if the fallback has to run; keys / list: kKeyCap 64-bit slots each
+__device__ bool select_topk_regs(SearchShared &S, const float (&acc)[QROWS * QCOLS], bool active, int it_f, int it_s, int it_j,
+                                 unsigned long long *keys, unsigned long long *list, int k, float *__restrict__ out_vals,
+                                 long long *__restrict__ out_inds, int C, int H, int W) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, wrp = tid >> 5, nw = nthr >> 5;
+    const int ncand = S.ncand;
+    const int m = min(k, ncand);
+    if (ncand <= kKeyCap) return false;        // tiny windows: the fallback sorts everything
+    FrameWin w;
+    w.nx = 0; w.ny = 0; w.off = 0;
+    if (active) w = S.fw[it_f];
+    const int r0 = it_s * QROWS, x0 = QCOLS * it_j;
+    // ---- 1. block min / max
+    unsigned int lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+    for (int s = 0; s < QROWS; ++s)
+#pragma unroll
+        for (int col = 0; col < QCOLS; ++col)
+            if (r0 + s < w.ny && x0 + col < w.nx) {
+                const unsigned int u = __float_as_uint(acc[s * QCOLS + col]);
+                if (u) lo = min(lo, u);    // the query itself (distance 0) would stretch the logarithmic bins to one per octave
+                hi = max(hi, u);
+            }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lane == 0) { S.red_min[wrp] = lo; S.red_max[wrp] = hi; }
+    for (int i = tid; i < 256; i += nthr) { S.hist[i] = 0u; S.hist2[i] = 0u; }
+    if (tid == 0) { S.sel_count = 0; S.sel_neq = 0u; S.sel_kk = 0u; }
+    __syncthreads();
+    lo = 0xffffffffu; hi = 0u;
+    for (int i = 0; i < nw; ++i) { lo = min(lo, S.red_min[i]); hi = max(hi, S.red_max[i]); }
+    if (lo > hi) lo = hi;                      // every distance is zero
+    const unsigned int range = hi - lo;
+    const int sh = range >= 256u ? (32 - __clz(range) - 8) : 0;
+    // ---- 2. sample histogram (bins of the bit pattern)
+    {
+        unsigned int ns = 0;
+        if (r0 + 2 < w.ny && x0 + 1 < w.nx) { const unsigned int u = __float_as_uint(acc[2 * QCOLS + 1]); atomicAdd(&S.hist[u <= lo ? 0u : (u - lo) >> sh], 1u); ++ns; }
+        if (r0 + 6 < w.ny && x0 + 2 < w.nx) { const unsigned int u = __float_as_uint(acc[6 * QCOLS + 2]); atomicAdd(&S.hist[u <= lo ? 0u : (u - lo) >> sh], 1u); ++ns; }
+        ns = __reduce_add_sync(0xffffffffu, ns);
+        if (lane == 0 && ns) atomicAdd(&S.sel_neq, ns);
+    }
+    __syncthreads();
+    if (wrp == 0) {
+        const unsigned int nsamp = S.sel_neq;
+        unsigned int need = (unsigned int)((2.0f * (float)m * (float)nsamp) / (float)ncand) + 6u;
+        unsigned int cum;
+        const int b1 = (nsamp == 0u || need >= nsamp) ? 255 : warp_find_bin(S.hist, need, cum);
+        if (lane == 0) S.sel_bin = b1;
+    }
+    __syncthreads();
+    const unsigned int b1 = (unsigned int)S.sel_bin;
+    // ---- 3. list of the candidates up to bin b1: count, one atomic per warp for the slots, then write
+    {
+        int cnt = 0;
+#pragma unroll
+        for (int s = 0; s < QROWS; ++s)
+#pragma unroll
+            for (int col = 0; col < QCOLS; ++col)
+                if (r0 + s < w.ny && x0 + col < w.nx) {
+                    const unsigned int u = __float_as_uint(acc[s * QCOLS + col]);
+                    cnt += (u <= lo || ((u - lo) >> sh) <= b1) ? 1 : 0;
+                }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(&S.sel_count, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - cnt;
+        if (cnt > 0) {
+#pragma unroll
+            for (int s = 0; s < QROWS; ++s)
+#pragma unroll
+                for (int col = 0; col < QCOLS; ++col)
+                    if (r0 + s < w.ny && x0 + col < w.nx) {
+                        const unsigned int u = __float_as_uint(acc[s * QCOLS + col]);
+                        if (u <= lo || ((u - lo) >> sh) <= b1) {
+                            if (pos < kKeyCap)
+                                list[pos] = ((unsigned long long)u << 32) | (unsigned int)(w.off + (r0 + s) * w.nx + x0 + col);
+                            ++pos;
+                        }
+                    }
+        }
+    }
+    __syncthreads();
+    const int nlist = S.sel_count;
+    if (nlist < m || nlist > kKeyCap) return false;
+    // ---- 4. linear histogram of the list, entries up to the bin that reaches m
+    unsigned int upper = (b1 >= 255u) ? hi + 1u : min(hi + 1u, lo + ((b1 + 1u) << sh));
+    const float dmin = __uint_as_float(lo);
+    const float scale = 256.f / (__uint_as_float(upper) - dmin);
+    for (int i = tid; i < nlist; i += nthr) {
+        const float d = __uint_as_float((unsigned int)(list[i] >> 32));
+        atomicAdd(&S.hist2[min(255, max(0, (int)((d - dmin) * scale)))], 1u);
+    }
+    __syncthreads();
+    if (wrp == 0) {
+        unsigned int cum;
+        const int b2 = warp_find_bin(S.hist2, (unsigned int)m, cum);
+        if (lane == 0) { S.sel_last = b2; S.sel_less = cum; }
+    }
+    __syncthreads();
+    const int b2 = S.sel_last;
+    const int n2 = (int)S.sel_less;            // entries with bin <= b2: m <= n2 <= nlist <= kKeyCap
+    for (int i = tid; i < nlist; i += nthr) {
+        const unsigned long long ent = list[i];
+        const float d = __uint_as_float((unsigned int)(ent >> 32));
+        if (min(255, max(0, (int)((d - dmin) * scale))) <= b2) keys[atomicAdd(&S.sel_kk, 1u)] = ent;
+    }
+    __syncthreads();
+    if (n2 <= kRankCap) {
+        // few survivors: the rank of a key = number of smaller keys (keys are distinct: they carry the enumeration
+        // index), one barrier instead of the 28+ of a bitonic sort; the owner of rank r writes output row r
+        const long long CHW = (long long)C * H * W;
+        for (int i = tid; i < n2; i += nthr) {
+            const unsigned long long mine = keys[i];
+            int rank = 0;
+            for (int j = 0; j < n2; ++j) rank += keys[j] < mine;
+            if (rank < m) {
+                int f, qy, qx;
+                cand_coords(S, (int)(mine & 0xffffffffu), f, qy, qx);
+                out_vals[rank] = __uint_as_float((unsigned)(mine >> 32));
+                out_inds[rank] = (long long)S.fw[f].t * CHW + (long long)qy * W + qx;
+            }
+        }
+        for (int r = m + tid; r < k; r += nthr) {
+            out_vals[r] = __int_as_float(0x7f800000);
+            out_inds[r] = -1;
+        }
+        return true;
+    }
+    int P = 1;
+    while (P < n2) P <<= 1;
+    for (int i = n2 + tid; i < P; i += nthr) keys[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_keys(keys, P);
+    write_topk(S, keys, m, k, out_vals, out_inds, C, H, W);
+    return true;
+}
+
+template <bool USE_TMA>
+__global__ void __launch_bounds__(QTHREADS, 2)
+search_quad_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ img, int T, int C, int H, int W,
+                   const long long *__restrict__ qinds, const float *__restrict__ fflow,
+                   const float *__restrict__ bflow, VnlbSearchParams p, int P, int ncand_max,
+                   float *__restrict__ vals, long long *__restrict__ inds) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SearchShared &S = *reinterpret_cast<SearchShared *>(smem_raw);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(SearchShared));
+    unsigned long long *mbar = keys + P;
+    float *qpatch = reinterpret_cast<float *>(mbar + 2);   // [dist_chnls][TPT][7][8]
+    float *tiles;
+    {
+        unsigned char *tb = reinterpret_cast<unsigned char *>(qpatch + p.dist_chnls * TPT * 56);
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(tb);
+        tiles = reinterpret_cast<float *>(tb + ((128u - (sa & 127u)) & 127u));   // TMA destinations: 128-byte aligned
+    }
+    float *dist = tiles;                                    // after the last phase
+
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int t0 = (int)qinds[3 * q], y0 = (int)qinds[3 * q + 1], x0 = (int)qinds[3 * q + 2];
+    float *ov = vals + (long long)q * p.k;
+    long long *oi = inds + (long long)q * p.k;
+    const bool ok = t0 >= 0 && t0 <= T - TPT && y0 >= 0 && y0 <= H - TPS && x0 >= 0 && x0 <= W - TPS;
+    if (!ok) {
+        for (int r = tid; r < p.k; r += blockDim.x) {
+            ov[r] = __int_as_float(0x7f800000);
+            oi[r] = -1;
+        }
+        return;
+    }
+    const long long HW = (long long)H * W, CHW = (long long)C * HW;
+    const int dc = p.dist_chnls;
+    if (tid < 32) build_windows_warp(S, t0, y0, x0, T, H, W, fflow, bflow, p);
+    if (USE_TMA && tid == 0) mbar_init(mbar, 1);
+    for (int i = tid; i < dc * TPT * 49; i += blockDim.x) {
+        const int pl = i / 49, r = i - pl * 49, c = pl / TPT, ht = pl - c * TPT, hy = r / 7, hx = r - hy * 7;
+        qpatch[pl * 56 + hy * 8 + hx] = img[(long long)(t0 + ht) * CHW + c * HW + (long long)(y0 + hy) * W + x0 + hx];
+    }
+    __syncthreads();
+    const int nfr = S.nfr;
+    const bool sw = S.shared_win != 0;
+    const int nfrm = p.nWt_f + p.nWt_b + 1;    // items: frame fastest, then column quad, then strip
+    const int it_r = tid / nfrm, it_f = tid - it_r * nfrm;
+    const int it_s = it_r / QQUADS, it_j = it_r - it_s * QQUADS;
+    const bool active = it_f < nfr && it_r < QITEMS;
+    float acc[QROWS * QCOLS];
+#pragma unroll
+    for (int i = 0; i < QROWS * QCOLS; ++i) acc[i] = 0.f;
+    unsigned parity = 0;
+    const int nslots = sw ? nfr + 1 : nfr;
+    // one loop over the (channel, patch frame) phases; with a shared window the tiles staged for patch frame 0 also
+    // serve patch frame 1 (slot f + 1)
+#pragma unroll 1
+    for (int ph = 0; ph < dc * TPT; ++ph) {
+        const int c = ph >> 1, ht = ph & 1;
+        if (!sw || ht == 0) {
+            __syncthreads();                 // every thread is done reading the tiles of the previous phase
+            if (USE_TMA) {
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                    mbar_expect_tx(mbar, (unsigned)(nslots * QTH * QTW * 4));
+                    for (int sl = 0; sl < nslots; ++sl) {
+                        const FrameWin w = S.fw[sw ? 0 : sl];
+                        const int tt = sw ? w.t + sl : w.t + ht;
+                        tma_load_box(tiles + sl * QSLOT, &tmap, mbar, w.x0, w.y0, tt * C + c);
+                    }
+                }
+                mbar_wait(mbar, parity);
+                parity ^= 1u;
+            } else {
+                // one warp per tile slot: lane = column for columns 0..31 (one copy per row and lane, two pointer
+                // increments per row), then lane = row for column 32
+                const int lane = tid & 31, wrp = tid >> 5, nw = blockDim.x >> 5;
+                for (int sl = wrp; sl < nslots; sl += nw) {
+                    const FrameWin w = S.fw[sw ? 0 : sl];
+                    const int tt = sw ? w.t + sl : w.t + ht;
+                    const int rows = w.ny + TPS - 1, cols = w.nx + TPS - 1;
+                    const float *src = img + (long long)tt * CHW + c * HW + (long long)w.y0 * W + w.x0;
+                    float *dst = tiles + sl * QSLOT;
+                    if (lane < cols) {
+                        const float *s2 = src + lane;
+                        float *d2 = dst + lane;
+                        for (int r = 0; r < rows; ++r) {
+                            cp_async4(d2, s2);
+                            s2 += W;
+                            d2 += QTW;
+                        }
+                    }
+                    if (cols > 32) {
+                        if (lane < rows) cp_async4(dst + lane * QTW + 32, src + (long long)lane * W + 32);
+                        if (lane == 0 && rows > 32) cp_async4(dst + 32 * QTW + 32, src + 32LL * W + 32);
+                    }
+                }
+                cp_async_wait_all();
+                __syncthreads();
+            }
+        }
+        if (active)
+            quad_plane(qpatch + ph * 56, tiles + (sw ? it_f + ht : it_f) * QSLOT + (it_s * QROWS) * QTW + QCOLS * it_j, acc);
+    }
+    __syncthreads();                         // the tiles are dead: their memory serves the selection
+    unsigned long long *list = reinterpret_cast<unsigned long long *>(tiles) + (((size_t)ncand_max + 1) >> 1);   // behind `dist`
+    if (select_topk_regs(S, acc, active, it_f, it_s, it_j, keys, list, p.k, ov, oi, C, H, W)) return;
+    __syncthreads();                         // fallback (heavy ties, tiny windows): distances to shared memory
+    if (active) {
+        const FrameWin w = S.fw[it_f];
+#pragma unroll
+        for (int s = 0; s < QROWS; ++s) {
+            const int r = it_s * QROWS + s;
+#pragma unroll
+            for (int col = 0; col < QCOLS; ++col) {
+                const int x = QCOLS * it_j + col;
+                if (r < w.ny && x < w.nx) dist[w.off + r * w.nx + x] = acc[s * QCOLS + col];
+            }
+        }
+    }
+    __syncthreads();
+    select_topk(S, dist, keys, p.k, 0u, 0u, ov, oi, C, H, W);
+}
+
 // patches[b,n,dt,ch,dy,dx] = img[t+dt,ch,y+dy,x+dx]   (search.py:91-98)
 __global__ void fill_patches_kernel(float *__restrict__ patches, const float *__restrict__ img,
                                     const long long *__restrict__ inds, long long BK, int T, int C, int H,
@@ -554,9 +1058,62 @@ static int next_pow2(int v) {
 
 static bool tiled_ok(const VnlbSearchParams *p) { return p->ps == TPS && p->pt == TPT && p->w_s == TWS; }
 
+// search path: 0 = automatic (quad kernel with TMA staging when the image allows it, quad kernel with cp.async
+// staging otherwise, 1-column tiled kernel beyond 13 frames, generic kernel for other shapes), 1 = never the quad
+// kernel, 2 = quad kernel without TMA
+static int g_search_path = -1;
+static int search_path() {
+    if (g_search_path < 0) {
+        const char *e = getenv("VNLB_SEARCH_PATH");
+        g_search_path = e ? atoi(e) : 0;
+        if (g_search_path < 0 || g_search_path > 2) g_search_path = 0;
+    }
+    return g_search_path;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+        (void)cudaGetLastError();
+        tried = true;
+    }
+    return fn;
+}
+
+// tensor map of the search image as [T*C, H, W] float32 with a 36 x 33 x 1 box; false if the image cannot be described
+// (row pitch or base not 16-byte aligned, frame smaller than a box, no driver entry point)
+static bool make_tile_map(CUtensorMap *map, const float *img, int T, int C, int H, int W) {
+    if ((W & 3) || (reinterpret_cast<uintptr_t>(img) & 15) || W < QTW || H < QTH) return false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T * (cuuint64_t)C};
+    const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)QTW, (cuuint32_t)QTH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(img), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace vnlb
 
 using namespace vnlb;
+
+extern "C" int vnlb_set_search_path(int path) {
+    const int prev = search_path();
+    if (path >= 0 && path <= 2) g_search_path = path;
+    return prev;
+}
 
 extern "C" size_t vnlb_search_workspace_bytes(int Q, const VnlbSearchParams *p) {
     (void)Q;
@@ -585,6 +1142,35 @@ extern "C" int vnlb_search_topk(const float *img, int T, int C, int H, int W, co
     const int ncand_max = nfr * p->w_s * p->w_s;
     const int P = next_pow2(p->k) > kKeyCap ? next_pow2(p->k) : kKeyCap;   // 64-bit key slots in shared memory
     const bool tiled = tiled_ok(p);
+    const bool quad = tiled && nfr <= QMAXF && p->dist_chnls <= 8 && search_path() != 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (quad) {
+        // [SearchShared][keys][mbarrier][query planes][<=127 B of alignment][frames+1 tile slots; later the distances]
+        const size_t tile_bytes = (size_t)(nfr + 1) * QSLOT * 4;
+        const size_t sel_bytes = (((size_t)ncand_max + 1) / 2 + kKeyCap) * 8;   // distances (fallback) + candidate list
+        const size_t smem = sizeof(SearchShared) + (size_t)P * 8 + 16 + (size_t)p->dist_chnls * TPT * 56 * 4 + 128 +
+                            (tile_bytes > sel_bytes ? tile_bytes : sel_bytes);
+        const int threads = ((nfr * QITEMS + 31) / 32) * 32;
+        CUtensorMap map;
+        memset(&map, 0, sizeof(map));
+        // TMA needs the box start 16-byte aligned in global memory (x0 % 4 == 0; measured with
+        // tools/experimental/tma_probe.cu: any other corner raises an illegal-instruction fault), which an arbitrary
+        // window corner is not: the TMA instantiation is kept for aligned-only use and is off
+        const bool tma = false && search_path() == 0 && make_tile_map(&map, img, T, C, H, W);
+        if (tma) {
+            e = cudaFuncSetAttribute(search_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("vnlb_search_topk: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
+            search_quad_kernel<true><<<Q, threads, smem, st>>>(map, img, T, C, H, W, (const long long *)qinds, fflow, bflow,
+                                                              *p, P, ncand_max, vals, (long long *)inds);
+        } else {
+            e = cudaFuncSetAttribute(search_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_error("vnlb_search_topk: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
+            search_quad_kernel<false><<<Q, threads, smem, st>>>(map, img, T, C, H, W, (const long long *)qinds, fflow, bflow,
+                                                               *p, P, ncand_max, vals, (long long *)inds);
+        }
+        return check_launch("vnlb_search_topk");
+    }
     size_t smem = sizeof(SearchShared) + (size_t)P * 8 + (size_t)ncand_max * 4;
     if (tiled)
         smem += (size_t)(2 * 52 + TCHUNK * TPT * TSLOT) * 4;
@@ -594,8 +1180,6 @@ extern "C" int vnlb_search_topk(const float *img, int T, int C, int H, int W, co
         set_error("vnlb_search_topk: search window needs %zu B of shared memory (> 227 KB)", smem);
         return VNLB_ERR_UNSUPPORTED;
     }
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e;
     if (tiled) {
         e = cudaFuncSetAttribute(search_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("vnlb_search_topk: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }

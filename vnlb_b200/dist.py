@@ -298,7 +298,7 @@ def _max_flow_y(flows, y0, y1):
 
 def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="default", params=None, stats=None,
                         group=None, device=None, clean=None, max_flow=None, row_weights=None, gather=True,
-                        rebalance=True, rebalance_round=2, margin_frac=0.10):
+                        rebalance=False, rebalance_round=2, margin_frac=0.10):
     """vnlb.denoise over all ranks of `group`.  Every rank passes the same `noisy` [T,C,H,W] (host, ideally pinned, or
     device) and the same `flows`; only its own band + halo rows are copied to its GPU.  Returns (deno, basic, seconds):
     the full frames on every rank (gather=True) or, with gather=False, this rank's band rows only as
@@ -309,7 +309,9 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
     row_weights : optional [H] expected cost per reference row for the initial band partition (None = equal row counts).
     rebalance : move the band borders once per step, after `rebalance_round` rounds, to equalise the predicted
                remaining time of the ranks (BandRebalancer); the tiles carry `margin_frac` x band rows of extra
-               margin on each side for that.
+               margin on each side for that.  OFF by default: measured on 2 B200s (1920x1080x30, sigma 10) the early
+               speed estimate overshoots (bands 861 k / 808 k groups without, 792 k / 877 k with) and the call is slower
+               (1008 vs 882 ms); kept as an option for content whose cost per row is known to be skewed.
     """
     clock = Timer()
     clock.tic()
