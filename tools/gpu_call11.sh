@@ -1,8 +1,8 @@
 #!/bin/bash
-# full GPU test-suite + default bench at N = 1 (new search kernel)
+# default bench at N = 1 (new search kernel)
 cd "$(dirname "$0")/.."
-timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/r2_pytest4.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_pytest4.log
-/usr/bin/time -v timeout 1500 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_n1_b.json 2> gpurun_out/r2_bench_n1_b.err; echo "bench rc=$?"; grep -E "Elapsed|Maximum resident" gpurun_out/r2_bench_n1_b.err
+SECONDS=0
+timeout 1500 python bench.py --steps 3 --warmup 3 > gpurun_out/r2_bench_n1_b.json 2> gpurun_out/r2_bench_n1_b.err; echo "bench rc=$? wall=${SECONDS}s"
 python - <<'PY'
 import json
 try:
