@@ -711,6 +711,294 @@ __device__ __forceinline__ void tridiag_regs2(float2 (&bl)[2 * ((NR + 3) / 4)], 
     for (int idx = lane; idx < R1 - R0; idx += 32) out[OREFL + R0 + idx] = sd[3 * KN + idx];
 }
 
+// ---------------------------------------------------------------------------------------------
+// COLUMNS SPLIT OVER THE WARPS, several rows per lane (the widest phase, 96 -> 64).  tridiag_regs is bound by the
+// shared-memory data pipe: every warp loads the broadcast operands (v, w, next x) of ALL live columns for ONE row per
+// lane (3 LDS.128 per 6 FFMA2; measured 70 % pipe utilisation at 35 % FMA).  Here warp h of 4 holds the 4-column chunks
+// I = h (mod 4) of the NR x NR trailing matrix for ALL rows, NS = NR / 32 rows per lane (rows l, l + 32, l + 64): the
+// three loads of a chunk feed 6 FFMA2 per row slot (18 for NS = 3), and each warp only loads its own quarter of the
+// columns -- 12 x less shared-memory traffic per FMA.  The per-row scalars of a step (x, r, y, v, w, the next x and r,
+// the 4-column window that supplies column c - 2) are kept REDUNDANTLY by every warp in the layout of tridiag_regs2
+// (shuffles fetch the rows c, c-1, c-2); what crosses warps are the partial sums of the mat-vec (part[warp][row], summed
+// in warp order by everybody after barrier B1), the published v / w / next x (warp h publishes row slot h, barrier B2)
+// and, every fourth step, the new window chunk from the warp that owns it.  Same arithmetic per element as
+// tridiag_regs2; only the grouping of the mat-vec partial sums differs.
+// Shared scratch (floats): xs[VL] vs[VL] ws[VL] part[4][NR] win[NR][4] d[KN] e[KN] tau[KN] reflectors.
+template <int QDG, int NR, int CEND> __host__ __device__ constexpr int tridiag_cols_scratch_floats() {
+    return 3 * (NR + 4) + 8 * NR + 3 * ((QDG - 1 - CEND - (QDG - NR) + 1 + 3) & ~3) +
+           ((refl_off(QDG, QDG - CEND) - refl_off(QDG, QDG - NR) + 3) & ~3);
+}
+
+template <int QDG, int NR, int CEND, int OPITCH, int OREFL>
+__device__ __forceinline__ void tridiag_cols(const float *Bm, int ldb, float *sv, float *out, float *trail, int lane, int h) {
+    constexpr int NS = NR / 32, NCH = NR / 4, NL = NCH / 4, VL = NR + 4;
+    constexpr int K0 = QDG - NR, K1 = QDG - 1 - CEND;
+    constexpr int KN = (K1 - K0 + 1 + 3) & ~3;
+    constexpr int R0 = refl_off(QDG, K0), R1 = refl_off(QDG, K1 + 1);
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(NS == 3 && NCH % 4 == 0 && CEND % 32 == 0 && CEND >= 32 && CEND < NR, "tridiag_cols: 96 rows in three slots, 4 warps");
+    float *xs = sv, *vs = sv + VL, *ws = sv + 2 * VL, *part = sv + 3 * VL, *win = part + 4 * NR;
+    float *sd = win + 4 * NR, *se = sd + KN, *st = se + KN, *srf = st + KN;
+    const uint32_t aX = smem_u32(xs), aV = smem_u32(vs), aW = smem_u32(ws);
+    int row[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) row[s] = lane + 32 * s;
+    // this lane's rows, this warp's column chunks
+    float2 b[NS][2 * NL];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int t = 0; t < NL; ++t) {
+            const float4 f = *reinterpret_cast<const float4 *>(Bm + row[s] * ldb + 4 * (4 * t + h));
+            b[s][2 * t] = make_float2(f.x, f.y);
+            b[s][2 * t + 1] = make_float2(f.z, f.w);
+        }
+    auto from_row = [&](int r, const float (&a)[NS]) -> float {
+        const int sl = r >> 5;
+        return __shfl_sync(FULL, sl == 0 ? a[0] : (sl == 1 ? a[1] : a[2]), r & 31);
+    };
+    constexpr int c0 = NR - 1;
+    float x[NS], r[NS], y[NS], wq[NS][4];
+    int Iw = (c0 - 2) >> 2;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const float x0 = Bm[row[s] * ldb + c0];
+        r[s] = Bm[row[s] * ldb + c0 - 1];
+        x[s] = row[s] < c0 ? x0 : 0.f;
+        const float4 f = *reinterpret_cast<const float4 *>(Bm + row[s] * ldb + 4 * Iw);
+        wq[s][0] = f.x; wq[s][1] = f.y; wq[s][2] = f.z; wq[s][3] = f.w;
+    }
+    float dk = Bm[c0 * ldb + c0];
+    for (int j = 32 * h + lane; j < 3 * VL; j += 128) sv[j] = 0.f;
+    __syncthreads();
+    if (h < NS) xs[row[h]] = x[h];
+    __syncthreads();
+    {   // partial y = B x over this warp's chunks, every row slot
+        float2 acc[NS][2];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc[s][0] = acc[s][1] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < NL; ++t) {
+            const float4 x4 = lds128(aX + 16 * (4 * t + h));
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                acc[s][0] = __ffma2_rn(b[s][2 * t], make_float2(x4.x, x4.y), acc[s][0]);
+                acc[s][1] = __ffma2_rn(b[s][2 * t + 1], make_float2(x4.z, x4.w), acc[s][1]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) part[h * NR + row[s]] = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
+    }
+    bool winload = false;
+    for (int c = NR - 1; c >= CEND; --c) {
+        const int k = NR - 1 - c;
+        __syncthreads();                                                       // B1: partial sums (and a new window) are published
+        if (winload) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const float4 f = *reinterpret_cast<const float4 *>(win + 4 * row[s]);
+                wq[s][0] = f.x; wq[s][1] = f.y; wq[s][2] = f.z; wq[s][3] = f.w;
+            }
+            winload = false;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            y[s] = (part[row[s]] + part[NR + row[s]]) + (part[2 * NR + row[s]] + part[3 * NR + row[s]]);
+        const float xBx = warp_sum(fmaf(x[2], y[2], fmaf(x[1], y[1], x[0] * y[0])));   // x = 0 on rows >= c
+        const float yc = from_row(c, y), ycm1 = from_row(c - 1, y), ycm2 = from_row(c - 2, y);
+        const float alpha = from_row(c - 1, x), bcc = from_row(c - 1, r);
+        const float xcm2 = from_row(c - 2, x), rcm2 = from_row(c - 2, r);
+        const float a2 = alpha * alpha;
+        const float nrm2 = fmaxf(yc, a2);
+        const bool skip = (nrm2 == a2);
+        const float rsq = rsqrt_approx(nrm2);
+        float sq = nrm2 * rsq;
+        sq = fmaf(0.5f * rsq, fmaf(-sq, sq, nrm2), sq);
+        const float beta = skip ? alpha : -copysignf(sq, alpha);
+        const float tau = skip ? 0.f : (beta - alpha) * rcp_newton(beta);
+        const float scale = skip ? 0.f : rcp_newton(alpha - beta);
+        const float ts = tau * scale;
+        const float uBu = fmaf(beta * beta, bcc, fmaf(-2.f * beta, ycm1, xBx));
+        const float hs = 0.5f * ts * ts * uBu;
+        const float wcm1 = fmaf(-hs, 1.f, ts * fmaf(-beta, bcc, ycm1));
+        const float vcm2 = xcm2 * scale;
+        const float wcm2 = fmaf(-hs, vcm2, ts * fmaf(-beta, rcm2, ycm2));
+        const int wsel = (c - 2) & 3;
+        float v[NS], w[NS], xn[NS], rn[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const bool act = row[s] < c;
+            v[s] = (row[s] == c - 1) ? 1.f : x[s] * scale;
+            w[s] = fmaf(-hs, v[s], ts * fmaf(-beta, r[s], y[s]));
+            if (!act) { v[s] = 0.f; w[s] = 0.f; }                              // dead rows: the update is a no-op
+            const float q = wsel == 0 ? wq[s][0] : (wsel == 1 ? wq[s][1] : (wsel == 2 ? wq[s][2] : wq[s][3]));
+            xn[s] = fmaf(-v[s], wcm1, fmaf(-w[s], 1.f, r[s]));
+            rn[s] = fmaf(-v[s], wcm2, fmaf(-w[s], vcm2, q));
+        }
+        if (h < NS) {                                                          // warp h publishes row slot h
+            const float pv = h == 0 ? v[0] : (h == 1 ? v[1] : v[2]), pw = h == 0 ? w[0] : (h == 1 ? w[1] : w[2]);
+            const float pxn = h == 0 ? xn[0] : (h == 1 ? xn[1] : xn[2]);
+            const int i = lane + 32 * h;
+            if (i < c) {
+                vs[i] = pv;
+                ws[i] = pw;
+                srf[refl_off(QDG, K0 + k) - R0 + (c - 1 - i)] = pv;
+                xs[i] = (i < c - 1) ? pxn : 0.f;
+            }
+            if (i == c) xs[i] = 0.f;
+        }
+        if (h == 3 && lane == 0) { sd[k] = dk; se[k] = beta; st[k] = tau; }
+        dk = from_row(c - 1, xn);                                              // B[c-1][c-1] after the update
+        __syncthreads();                                                       // B2: v, w and the next x are published
+        {
+            float2 nv[NS], nw[NS], acc[NS][2];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                nv[s] = make_float2(-v[s], -v[s]);
+                nw[s] = make_float2(-w[s], -w[s]);
+                acc[s][0] = acc[s][1] = make_float2(0.f, 0.f);
+            }
+            const int nlive = (c + 3) >> 2;                                    // chunks holding a column < c
+            const int tl = nlive > h ? (nlive - h + 3) >> 2 : 0;               // ... of this warp
+#define VNLB_C1(T)                                                                       \
+            {                                                                           \
+                constexpr int t = (T) < NL ? (T) : 0;                                   \
+                const int I = 4 * t + h;                                                \
+                const float4 v4 = lds128(aV + 16 * I), w4 = lds128(aW + 16 * I), x4 = lds128(aX + 16 * I);                        \
+                const float2 v01 = make_float2(v4.x, v4.y), v23 = make_float2(v4.z, v4.w);                                          \
+                const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);                                          \
+                const float2 x01 = make_float2(x4.x, x4.y), x23 = make_float2(x4.z, x4.w);                                          \
+                _Pragma("unroll") for (int s = 0; s < NS; ++s) {                        \
+                    b[s][2 * t] = __ffma2_rn(nv[s], w01, __ffma2_rn(nw[s], v01, b[s][2 * t]));                                      \
+                    b[s][2 * t + 1] = __ffma2_rn(nv[s], w23, __ffma2_rn(nw[s], v23, b[s][2 * t + 1]));                              \
+                    acc[s][0] = __ffma2_rn(b[s][2 * t], x01, acc[s][0]);                \
+                    acc[s][1] = __ffma2_rn(b[s][2 * t + 1], x23, acc[s][1]);            \
+                }                                                                       \
+            }
+            static_assert(NL == 6, "tridiag_cols: the sweep is written for 6 chunks per warp");
+            switch (tl) {
+                case 6: VNLB_C1(5)
+                case 5: VNLB_C1(4)
+                case 4: VNLB_C1(3)
+                case 3: VNLB_C1(2)
+                case 2: VNLB_C1(1)
+                case 1: VNLB_C1(0)
+                default: break;
+            }
+#undef VNLB_C1
+            {   // the window copies get the same update
+                const float4 v4 = lds128(aV + 16 * Iw), w4 = lds128(aW + 16 * Iw);
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    wq[s][0] = fmaf(-v[s], w4.x, fmaf(-w[s], v4.x, wq[s][0])); wq[s][1] = fmaf(-v[s], w4.y, fmaf(-w[s], v4.y, wq[s][1]));
+                    wq[s][2] = fmaf(-v[s], w4.z, fmaf(-w[s], v4.z, wq[s][2])); wq[s][3] = fmaf(-v[s], w4.w, fmaf(-w[s], v4.w, wq[s][3]));
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) part[h * NR + row[s]] = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
+        }
+        if (((c - 3) >> 2) != Iw) {                                            // next step needs column c-3: its owner publishes the chunk
+            Iw = (c - 3) >> 2;
+            if ((Iw & 3) == h) {
+                switch (Iw >> 2) {
+#define VNLB_CW(T) case (T): { constexpr int t = (T) < NL ? (T) : 0; _Pragma("unroll") for (int s = 0; s < NS; ++s)                \
+                        *reinterpret_cast<float4 *>(win + 4 * row[s]) = make_float4(b[s][2 * t].x, b[s][2 * t].y, b[s][2 * t + 1].x, b[s][2 * t + 1].y); } break;
+                    VNLB_CW(0) VNLB_CW(1) VNLB_CW(2) VNLB_CW(3) VNLB_CW(4) VNLB_CW(5)
+#undef VNLB_CW
+                    default: break;
+                }
+            }
+            winload = true;
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            x[s] = (row[s] < c - 1) ? xn[s] : 0.f;
+            r[s] = rn[s];
+        }
+    }
+    {   // trailing CEND x CEND matrix for the next phase: row i at trail + i * CEND
+#pragma unroll
+        for (int s = 0; s < CEND / 32; ++s)
+#pragma unroll
+            for (int t = 0; t < CEND / 16; ++t)
+                *reinterpret_cast<float4 *>(trail + row[s] * CEND + 4 * (4 * t + h)) =
+                    make_float4(b[s][2 * t].x, b[s][2 * t].y, b[s][2 * t + 1].x, b[s][2 * t + 1].y);
+    }
+    __syncthreads();
+    constexpr int NK = K1 - K0 + 1;
+    const int tid = 32 * h + lane;
+    for (int idx = tid; idx < NK; idx += 128) {
+        out[K0 + idx] = sd[idx];
+        out[OPITCH + K0 + idx] = se[idx];
+        out[2 * OPITCH + K0 + idx] = st[idx];
+    }
+    for (int idx = tid; idx < R1 - R0; idx += 128) out[OREFL + R0 + idx] = srf[idx];
+}
+
+// The first QDG - NR Householder steps on the symmetric matrix M (shared memory, pitch ld, index-reversed like
+// everywhere here): plain three-pass steps (v; p = M v; rank-2 update), one thread per row -- two steps of 98 before
+// tridiag_cols takes the 96 x 96 rest.  Same d / e / tau / reflector conventions as tridiag_regs.
+template <int QDG, int NR, int OPITCH, int OREFL>
+__device__ __forceinline__ void tridiag_head_smem(float *M, int ld, float *scr, float *out, int tid) {
+    float *vs = scr, *ws = scr + ld, *red = scr + 2 * ld;
+    int phase = 0;
+    // block sum in LOGICAL warp order (tid = 32 * logical warp + lane): the result must not depend on warp_rotation()
+    auto block_sum = [&](float v, float *rd, int &ph) -> float {
+        v = warp_sum(v);
+        float *r = rd + 4 * ph;
+        if ((tid & 31) == 0) r[tid >> 5] = v;
+        __syncthreads();
+        ph ^= 1;
+        return (r[0] + r[1]) + (r[2] + r[3]);
+    };
+    for (int k = 0; k < QDG - NR; ++k) {
+        const int c = QDG - 1 - k;
+        const bool act = tid < c;
+        const float x = act ? M[tid * ld + c] : 0.f;
+        const float alpha = M[(c - 1) * ld + c], dk = M[c * ld + c];
+        const float ssq = block_sum((act && tid != c - 1) ? x * x : 0.f, red, phase);
+        float *refl = out + OREFL + refl_off(QDG, k);
+        if (ssq == 0.f) {                          // nothing to annihilate: H = I
+            if (tid == 0) { out[k] = dk; out[OPITCH + k] = alpha; out[2 * OPITCH + k] = 0.f; }
+            if (act) refl[c - 1 - tid] = (tid == c - 1) ? 1.f : 0.f;
+            continue;
+        }
+        const float beta = -copysignf(sqrtf(fmaf(alpha, alpha, ssq)), alpha);
+        const float tau = (beta - alpha) / beta;
+        const float scale = 1.f / (alpha - beta);
+        const float v = act ? ((tid == c - 1) ? 1.f : x * scale) : 0.f;
+        if (tid < ld) vs[tid] = v;
+        if (act) refl[c - 1 - tid] = v;
+        if (tid == 0) { out[k] = dk; out[OPITCH + k] = beta; out[2 * OPITCH + k] = tau; }
+        __syncthreads();
+        float p = 0.f;
+        if (act) {
+            const float *mr = M + tid * ld;
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+            for (int j = 0; j < c; j += 4) {       // vs[j] = 0 for j >= c; the pitch covers the last chunk
+                const float4 m4 = *reinterpret_cast<const float4 *>(mr + j), v4 = *reinterpret_cast<const float4 *>(vs + j);
+                p0 = fmaf(m4.x, v4.x, p0); p1 = fmaf(m4.y, v4.y, p1); p2 = fmaf(m4.z, v4.z, p2); p3 = fmaf(m4.w, v4.w, p3);
+            }
+            p = (p0 + p1) + (p2 + p3);
+        }
+        const float sdot = block_sum(act ? p * v : 0.f, red, phase);
+        const float w = act ? fmaf(-0.5f * tau * tau * sdot, v, tau * p) : 0.f;
+        if (tid < ld) ws[tid] = w;
+        __syncthreads();
+        if (act) {
+            float *mr = M + tid * ld;
+            for (int j = 0; j < c; j += 4) {
+                float4 m4 = *reinterpret_cast<float4 *>(mr + j);
+                const float4 v4 = *reinterpret_cast<const float4 *>(vs + j), w4 = *reinterpret_cast<const float4 *>(ws + j);
+                m4.x = fmaf(-v, w4.x, fmaf(-w, v4.x, m4.x)); m4.y = fmaf(-v, w4.y, fmaf(-w, v4.y, m4.y));
+                m4.z = fmaf(-v, w4.z, fmaf(-w, v4.z, m4.z)); m4.w = fmaf(-v, w4.w, fmaf(-w, v4.w, m4.w));
+                *reinterpret_cast<float4 *>(mr + j) = m4;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // Workspace per problem (floats): d[LDG] e[LDG] tau[LDG] mean[LDG] reflectors[nref] trailing matrix[NR2 x NR2];
 // tau[LDG-1] doubles as the "problem is valid" flag between the kernels of the split path.
 constexpr int SPLIT_NR2 = 64;                      // trailing size handed from phase 1 to phase 2
@@ -894,6 +1182,173 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
     }
     float *bs_row = nullptr;
     tridiag_regs<QD, QD, SPLIT_NR2, TT, NRC>(b, sv, wsp, wsp + split_trail_off<QD>(), tid, smem_u32(bs_row));
+}
+
+// cov_tridiag_kernel with the elimination 98 -> 64 done by tridiag_head_smem (two steps) + tridiag_cols (columns split over
+// the warps, three rows per lane) instead of tridiag_regs: the matrix stays in shared memory until the warps have
+// taken their register tiles.  Same workspace contents (to rounding).
+constexpr int COLS_NR = 96;
+template <bool FUSED, int QD>
+__global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) {
+    constexpr int NRC = (QD + 3) / 4;
+    constexpr int LDQ = (QD + 3) & ~3, NCH = LDQ / 4;
+    extern __shared__ __align__(16) float sm[];
+    const VnlbBayesParams &P = a.P;
+    const int n = P.k, ps = P.ps, ps2 = ps * ps, C = P.c;
+    const int lane = threadIdx.x & 31, warp = ((threadIdx.x >> 5) + warp_rotation()) & (TT / 32 - 1), tid = 32 * warp + lane;
+    const int g = blockIdx.x / C, ch = blockIdx.x - g * C;
+    float *wsp = a.ws + (size_t)blockIdx.x * a.ws_stride;
+    const bool valid_row = !a.inds || row_valid_block(a.inds + (long long)g * n, n);
+    if (threadIdx.x == 0) wsp[3 * LDQ - 1] = valid_row ? 1.f : 0.f;   // flag for tridiag_tail_kernel
+    if (!valid_row) return;
+    float *Y = sm;                                   // Y[n][LDQ]: patches, columns reversed (column j = patch element QD-1-j)
+    const int ybody = max(n, LDQ) * LDQ + tridiag_cols_scratch_floats<QD, COLS_NR, SPLIT_NR2>();   // patches / the matrix, then the scratch
+    int *pb = (int *)(sm + ybody + 8);               // fused: offset of the patch corner in the image (8 floats of slack: tile reads)
+    float *sv = sm + max(n, LDQ) * LDQ;              // scratch of the tridiagonalisation, behind the matrix
+    const int rstride = P.pt * C * ps2;
+    const long long HW = (long long)a.H * a.W, CHW = HW * C;
+    if (FUSED) {
+        int bad = 0;
+        for (int nn = tid; nn < n; nn += TT) {
+            int t, y, x;
+            decode_ind(a.inds[(long long)g * n + nn], a.H, a.W, C, t, y, x);
+            bad |= (t < 0 || t + P.pt > a.T || y + ps > a.H || x + ps > a.W);
+            pb[nn] = (int)((long long)t * CHW + (long long)y * a.W + x);
+        }
+        if (__syncthreads_or(bad)) {                 // malformed index: the group is skipped (bayes_kernel does the same)
+            if (threadIdx.x == 0) wsp[3 * LDQ - 1] = 0.f;
+            return;
+        }
+    }
+    auto col_off = [&](int j) -> int {
+        const int dt = j / ps2, r = j - dt * ps2;
+        if (FUSED) { const int dy = r / ps, dx = r - dy * ps; return (int)(dt * CHW + ch * HW + (long long)dy * a.W + dx); }
+        return (dt * C + ch) * ps2 + r;
+    };
+    const float *src = FUSED ? (P.cov_from_basic ? a.img_basic : a.img_noisy)
+                             : (P.cov_from_basic ? a.pbasic : a.pnoisy) + (long long)g * n * rstride;
+    int co[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) co[q] = col_off(min(lane + 32 * q, QD - 1));
+    // ---- stage all n patches (every load independent: one exposed latency)
+    constexpr int SU = 5;                            // patches in flight per warp (20 independent loads per lane)
+    for (int n0 = warp; n0 < n; n0 += SU * (TT / 32)) {
+        float vals[SU][4];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int nn = min(n0 + u * (TT / 32), n - 1);
+            const float *q = src + (FUSED ? (long long)pb[nn] : (long long)nn * rstride);
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) vals[u][qq] = (lane + 32 * qq < QD) ? q[co[qq]] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int nn = n0 + u * (TT / 32);
+            if (nn < n) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int j = lane + 32 * qq;
+                    if (j < QD) Y[nn * LDQ + (QD - 1 - j)] = vals[u][qq];
+                    else if (j < LDQ) Y[nn * LDQ + j] = 0.f;                         // zero pad columns QD..LDQ-1
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- centre (same summation order as bayes_kernel: 4 interleaved partial sums)
+    const float inv_n = 1.f / (float)n;
+    if (tid < LDQ) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int nn = 0;
+        for (; nn + 3 < n; nn += 4) {
+            s0 += Y[nn * LDQ + tid]; s1 += Y[(nn + 1) * LDQ + tid];
+            s2 += Y[(nn + 2) * LDQ + tid]; s3 += Y[(nn + 3) * LDQ + tid];
+        }
+        for (; nn < n; ++nn) s0 += Y[nn * LDQ + tid];
+        const float mj = ((s0 + s1) + (s2 + s3)) * inv_n;
+        for (nn = 0; nn < n; ++nn) Y[nn * LDQ + tid] -= mj;
+        if (tid < QD) wsp[3 * LDQ + (QD - 1 - tid)] = mj; else wsp[3 * LDQ + tid] = 0.f;
+    }
+    __syncthreads();
+    // ---- covariance: 8 x 8 register tiles of the lower triangle, accumulated over the patches in order (entries
+    //      bit-identical to bayes_kernel).  The kernel is bound by the shared-memory data pipe (ncu: 73-79 % busy), so the
+    //      covariance is formed where a loaded operand feeds most FMAs (4 LDS.128 per 32 FFMA2), then mirrored through
+    //      shared memory into the row-per-thread register layout of the tridiagonalisation.
+    static_assert(NRC == NCH, "cov_tridiag_kernel: rows fully in registers");
+    constexpr int NT8 = (LDQ + 7) / 8, NTRI = NT8 * (NT8 + 1) / 2;
+    static_assert(NTRI <= TT, "one 8 x 8 tile per thread");
+    int ti = -1, tj = 0;
+    if (tid < NTRI) {
+        ti = (int)((sqrtf(8.f * tid + 1.f) - 1.f) * 0.5f);
+        while (ti * (ti + 1) / 2 > tid) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= tid) ++ti;
+        tj = tid - ti * (ti + 1) / 2;
+    }
+    {
+        float2 acc[8][4];
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa)
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) acc[aa][bb] = make_float2(0.f, 0.f);
+        if (ti >= 0) {
+            const float *ra = Y + 8 * ti, *rb = Y + 8 * tj;      // (columns >= LDQ of the last tile read the next row: never stored)
+            for (int nn = 0; nn < n; ++nn) {
+                const float4 a0 = *reinterpret_cast<const float4 *>(ra + nn * LDQ), a1 = *reinterpret_cast<const float4 *>(ra + nn * LDQ + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(rb + nn * LDQ), b1 = *reinterpret_cast<const float4 *>(rb + nn * LDQ + 4);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float2 c0 = make_float2(b0.x, b0.y), c1 = make_float2(b0.z, b0.w), c2 = make_float2(b1.x, b1.y), c3 = make_float2(b1.z, b1.w);
+#pragma unroll
+                for (int aa = 0; aa < 8; ++aa) {
+                    const float2 ad = make_float2(av[aa], av[aa]);
+                    acc[aa][0] = __ffma2_rn(ad, c0, acc[aa][0]); acc[aa][1] = __ffma2_rn(ad, c1, acc[aa][1]);
+                    acc[aa][2] = __ffma2_rn(ad, c2, acc[aa][2]); acc[aa][3] = __ffma2_rn(ad, c3, acc[aa][3]);
+                }
+            }
+        }
+        __syncthreads();                             // Y is dead: its place takes the full symmetric matrix A[LDQ][LDQ]
+        if (ti >= 0) {
+            float *A = Y;
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) {         // rows 8 ti + aa, columns 8 tj .. 8 tj + 7
+                const int i = 8 * ti + aa;
+                if (i < LDQ) {
+                    *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
+                    if (8 * tj + 4 < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
+                }
+            }
+#pragma unroll
+            for (int bb = 0; bb < 8; ++bb) {         // mirrored: rows 8 tj + bb, columns 8 ti .. 8 ti + 7
+                const int j = 8 * tj + bb;
+                if (j < LDQ) {
+                    float cv[8];
+#pragma unroll
+                    for (int aa = 0; aa < 8; ++aa) cv[aa] = ((bb & 1) ? acc[aa][bb >> 1].y : acc[aa][bb >> 1].x) * inv_n;
+                    *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti) = make_float4(cv[0], cv[1], cv[2], cv[3]);
+                    if (8 * ti + 4 < LDQ) *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float dg = (tid < QD) ? Y[tid * LDQ + tid] : 0.f;   // diagonal entry (already divided by n)
+    if (a.dbg_mat) {                                 // parity hook: the covariance in natural (un-reversed) index order
+        float *o = a.dbg_mat + (size_t)blockIdx.x * QD * QD;
+        for (int idx = threadIdx.x; idx < QD * QD; idx += TT) {
+            const int i = idx / QD, j = idx - i * QD;
+            o[idx] = Y[(QD - 1 - i) * LDQ + (QD - 1 - j)];
+        }
+    }
+    if (a.rank_var) {                                // rank_var = mean over channels of trace(C) (bayes_est.py:39-40)
+        float tr = warp_sum(dg);
+        float *red = (float *)(pb + ((n + 3) & ~3));
+        if (lane == 0) red[warp] = tr;
+        __syncthreads();
+        if (tid == 0) atomicAdd(&a.rank_var[g], ((red[0] + red[1]) + (red[2] + red[3])) / (float)C);
+    }
+    __syncthreads();
+    tridiag_head_smem<QD, COLS_NR, LDQ, 4 * LDQ>(Y, LDQ, sv, wsp, tid);
+    tridiag_cols<QD, COLS_NR, SPLIT_NR2, LDQ, 4 * LDQ>(Y, LDQ, sv, wsp, wsp + split_trail_off<QD>(), lane, warp);
 }
 
 // Split path, later phases of the tridiagonalisation: the NR x NR trailing matrix comes from the workspace (float
@@ -2085,8 +2540,15 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         // registers + the dying columns in shared memory, 128 registers, 4 CTAs per SM) measured 1.5 % SLOWER: this phase is
         // bound by FFMA2 / LDS throughput, not by occupancy (profiles/r1_summary.md).
         constexpr int NCHQ = (QD + 3) / 4;
-        const size_t smem1 = (size_t)(ybody + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
-        auto k1 = cov_tridiag_kernel<FUSED, QD, NCHQ>;
+        size_t smem1 = (size_t)(ybody + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
+        // VNLB_COV4=1: elimination 98 -> 64 with the columns split over the warps (cov_tridiag4_kernel).  Parity-green and
+        // 12 x less shared-memory traffic per FMA in the sweep, but the per-row scalar work is replicated in every warp
+        // (5.1e8 vs 4.0e8 warp instructions per 2048 groups): 14.58 vs 14.74 ms per 16384 groups, i.e. within 1 % of
+        // tridiag_regs (profiles/r2_summary.md).  Off by default.
+        static const int cols4 = []() { const char *e4 = getenv("VNLB_COV4"); return (e4 && e4[0] == '1') ? 1 : 0; }();
+        const size_t smem1_4 = (size_t)(yrows * 100 + tridiag_cols_scratch_floats<QD, COLS_NR, SPLIT_NR2>() + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
+        auto k1 = cols4 ? cov_tridiag4_kernel<FUSED, QD> : cov_tridiag_kernel<FUSED, QD, NCHQ>;
+        if (cols4) smem1 = smem1_4;
         constexpr int LDG = (QD + 3) & ~3;
         auto k1b = tridiag_tail_kernel<QD, SPLIT_NR2, SPLIT_NR3, 64, 8, LDG, 4 * LDG, split_trail_off<QD>(), split_trail2_off<QD>()>;
         auto k1c = tridiag_tail_kernel<QD, SPLIT_NR3, 2, 32, 16, LDG, 4 * LDG, split_trail2_off<QD>(), 0>;
