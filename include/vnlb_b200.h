@@ -158,6 +158,18 @@ int vnlb_select_queries(int8_t *mask, int T, int H, int W, double prob, uint32_t
 int vnlb_round_dedup(const int64_t *qinds, int64_t *inds, int B, int K, uint32_t *owner, uint32_t round,
                      int8_t *mask, int T, int C, int H, int W, int boost, uint32_t *dropped, void *stream);
 
+/* Device-controlled round of the throughput schedule (what a CUDA graph of a round replays): one call = zero the
+ * counters, advance the round index state[0] (uint32 in device memory, zeroed by the caller at the start of a step),
+ * count the masked pixels (counters[0]), draw -- the probability is computed on the device from that live count with the
+ * rule of the host loop: target = clamp(remaining * frac, qmin, (rows - 256) / 1.25), expected draw 0.97 target -- and
+ * pad qinds ([rows,3]) with invalid queries beyond counters[1].  No scalar of the call depends on the round, so the
+ * launches can be captured once and replayed.  vnlb_round_dedup_dev is vnlb_round_dedup with the round read from
+ * state[0] - 1. */
+int vnlb_round_draw(int8_t *mask, int T, int H, int W, double frac, int qmin, int rows, uint32_t seed,
+                    uint32_t *state, int64_t *qinds, uint32_t *counters, void *stream);
+int vnlb_round_dedup_dev(const int64_t *qinds, int64_t *inds, int B, int K, uint32_t *owner, const uint32_t *state,
+                         int8_t *mask, int T, int C, int H, int W, int boost, uint32_t *dropped, void *stream);
+
 /* exec_flat_areas, lib/vnlb/utils/flat_areas.py:16-34.  flat: uint8 [B]
  * (0/1), written for every row (invalid rows get 0). thresh = gamma*sigma2. */
 int vnlb_flat_areas(const float *pnoisy, const int64_t *inds, uint8_t *flat, int B, int K,

@@ -46,6 +46,20 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert rc == _lib.ERR_BAD_ARG
 
 
+def test_round_draw_rejects_bad_arguments_without_a_gpu():
+    from vnlb_b200 import _lib
+    n0 = int(_lib.lib.vnlb_kernel_launches())
+    rc = _lib.lib.vnlb_round_draw(ctypes.c_void_p(8), 2, 8, 8, 0.0, 16, 64, 1, ctypes.c_void_p(8), ctypes.c_void_p(8),
+                                  ctypes.c_void_p(8), None)
+    assert rc == _lib.ERR_BAD_ARG and b"vnlb_round_draw" in _lib.lib.vnlb_last_error()
+    rc = _lib.lib.vnlb_round_dedup_dev(ctypes.c_void_p(8), ctypes.c_void_p(8), 4, 4, ctypes.c_void_p(8), None,
+                                       ctypes.c_void_p(8), 2, 3, 8, 8, 1, ctypes.c_void_p(8), None)
+    assert rc == _lib.ERR_BAD_ARG
+    assert int(_lib.lib.vnlb_kernel_launches()) == n0
+    prev = _lib.lib.vnlb_set_search_path(1)
+    assert prev in (0, 1, 2) and _lib.lib.vnlb_set_search_path(prev) == 1
+
+
 def test_switches_and_counters_without_a_gpu():
     """vnlb_set_bayes_split returns the previous setting; vnlb_kernel_launches is a monotonic counter (0 launches here)."""
     from vnlb_b200 import _lib

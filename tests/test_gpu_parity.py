@@ -872,3 +872,57 @@ def test_constant_video_is_a_fixed_point(vb):
         deno, basic, _ = vb.denoise(vid, 20., schedule=sched, verbose=False)
         # exact ties concentrate thousands of patches on the first candidates of each window: fp32 sums of ~1e6
         assert np.abs(basic.cpu().numpy() - vid).max() < 5e-2 and np.abs(deno.cpu().numpy() - vid).max() < 5e-2
+
+
+# ---------------------------------------------------------------- device-controlled rounds / CUDA graphs
+def test_round_draw_is_a_device_side_draw(vb):
+    """vnlb_round_draw: counts the mask, draws with the on-device probability (target = clamp(remaining * frac, qmin,
+    (rows - 256) / 1.25), expected 0.97 target), consumes the drawn pixels, pads the rest of qinds, advances the round."""
+    from vnlb_b200 import _lib as L
+    from vnlb_b200 import mask as gm
+    T, H, W = 6, 96, 128
+    m, nset = gm.init_mask((T, 3, H, W), gargs(vb, 0), DEV)
+    before = m.clone()
+    rows = 2048
+    q = torch.zeros((rows, 3), dtype=torch.int64, device=DEV)
+    cnt = torch.full((2,), 77, dtype=torch.int32, device=DEV)
+    state = torch.zeros((4,), dtype=torch.int32, device=DEV)
+    for rnd in range(2):
+        L.check(L.lib.vnlb_round_draw(L.ptr(m), T, H, W, 0.125, 64, rows, 123, L.ptr(state), L.ptr(q), L.ptr(cnt), None), "draw")
+        torch.cuda.synchronize()
+        remaining, nsel = int(cnt[0]), int(cnt[1])
+        assert int(state[0]) == rnd + 1
+        assert remaining == int(before.sum())
+        target = min((rows - 256) * 4 // 5, max(64, int(remaining * 0.125)))
+        assert abs(nsel - 0.97 * target) < 6 * target ** 0.5 + 1
+        qq = q.cpu().numpy()
+        assert np.all(qq[nsel:] == -1) and np.all(qq[:nsel, 0] >= 0)
+        sel = before[qq[:nsel, 0], qq[:nsel, 1], qq[:nsel, 2]].cpu().numpy()
+        assert np.all(sel == 1)                                             # drawn pixels were masked ...
+        assert len({tuple(r) for r in qq[:nsel]}) == nsel                   # ... distinct ...
+        assert int(m.sum()) == remaining - nsel                             # ... and are consumed
+        before = m.clone()
+
+
+@pytest.mark.parametrize("sigma", [20.])
+def test_graph_rounds_match_eager_rounds(vb, sigma):
+    """fast_graph: the rounds of a step replayed from CUDA graphs (device-controlled draw) against the eager two-stream
+    loop: same algorithm, the draw probability comes from the live instead of the two-rounds-old count, so the
+    processed pixels differ slightly -- final / basic PSNR within 0.02 dB, group counts within 3 %, and two graph runs
+    process exactly the same number of groups (deterministic)."""
+    from vnlb_b200 import synth
+    T, H, W = 8, 192, 256
+    clean, flows = synth.synth_video(T, H, W, 7, return_flows=True)
+    noisy = synth.add_noise(clean, sigma, 7)
+    out = {}
+    for name, graph in (("eager", False), ("graph", True), ("graph2", True)):
+        params = vb.get_params(sigma)
+        params["fast_graph"] = [graph, graph]
+        st = {}
+        d, b, _ = vb.denoise(noisy, sigma, verbose=False, flows=flows, params=params, stats=st)
+        out[name] = (float(vb.compute_psnrs(d.cpu().numpy(), clean).mean()), float(vb.compute_psnrs(b.cpu().numpy(), clean).mean()),
+                     st["ngroups"], st["nrounds"])
+    assert abs(out["graph"][0] - out["eager"][0]) < 0.02 and abs(out["graph"][1] - out["eager"][1]) < 0.02, out
+    for a, b_ in zip(out["graph"][2], out["eager"][2]):
+        assert abs(a - b_) <= 0.03 * b_, out
+    assert out["graph"][2][0] == out["graph2"][2][0], out                  # step 1 is bit-deterministic (step 2 reads float-atomic sums)

@@ -36,7 +36,7 @@ EXPORTS = [
     "vnlb_kernel_launches",
     "vnlb_last_error", "vnlb_version", "vnlb_rgb2yuv", "vnlb_yuv2rgb", "vnlb_init_mask", "vnlb_init_mask_tile",
     "vnlb_set_search_path", "vnlb_search_workspace_bytes", "vnlb_search_topk", "vnlb_fill_patches", "vnlb_mask_update",
-    "vnlb_count_mask", "vnlb_select_queries", "vnlb_pad_queries", "vnlb_round_dedup",
+    "vnlb_count_mask", "vnlb_select_queries", "vnlb_pad_queries", "vnlb_round_dedup", "vnlb_round_draw", "vnlb_round_dedup_dev",
     "vnlb_flat_areas", "vnlb_bayes_workspace_bytes", "vnlb_bayes_filter", "vnlb_bayes_debug", "vnlb_bayes_matrix_dim", "vnlb_bayes_fused_supported", "vnlb_set_bayes_split", "vnlb_bayes_aggregate_fused", "vnlb_aggregate",
     "vnlb_normalize",
 ]
@@ -69,6 +69,8 @@ lib.vnlb_count_mask.argtypes = [_vp, _i, _i, _i, _vp, _vp]
 lib.vnlb_select_queries.argtypes = [_vp, _i, _i, _i, ctypes.c_double, ctypes.c_uint32, ctypes.c_uint32, _vp, _i, _vp, _vp]
 lib.vnlb_pad_queries.argtypes = [_vp, _vp, _i, _vp]
 lib.vnlb_round_dedup.argtypes = [_vp, _vp, _i, _i, _vp, ctypes.c_uint32, _vp, _i, _i, _i, _i, _i, _vp, _vp]
+lib.vnlb_round_draw.argtypes = [_vp, _i, _i, _i, ctypes.c_double, _i, _i, ctypes.c_uint32, _vp, _vp, _vp, _vp]
+lib.vnlb_round_dedup_dev.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]
 lib.vnlb_flat_areas.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]
 lib.vnlb_bayes_workspace_bytes.argtypes = [_i, ctypes.POINTER(BayesParams)]
 lib.vnlb_bayes_filter.argtypes = [_vp, _vp, _vp, _vp, _i, ctypes.POINTER(BayesParams), _vp, _vp, _sz, _vp]

@@ -169,6 +169,58 @@ __global__ void select_queries_kernel(int8_t *__restrict__ mask, int T, int H, i
     }
 }
 
+// ---------------------------------------------------------------------------
+// Device-controlled round (vnlb_round_draw): the draw probability is computed ON THE DEVICE from the live count of
+// masked pixels, and the round index lives in device memory, so the kernel sequence of a round has no host-computed
+// scalar left -- it can be captured once in a CUDA graph and replayed for every round of a step.
+// state[0] = rounds drawn so far in this step (the current round is state[0] - 1 after round_begin_kernel).
+// ---------------------------------------------------------------------------
+__global__ void round_begin_kernel(unsigned int *state, unsigned int *counters) {
+    counters[0] = 0u;
+    counters[1] = 0u;
+    state[0] += 1u;
+}
+
+__device__ __forceinline__ unsigned int draw_threshold(unsigned int remaining, float frac, int qmin, int rows) {
+    // same rule as the host loop of schedule.py: target = clamp(remaining * frac, qmin, rows'), expected draw 0.97 target
+    const int cap_target = max(1, (int)(((long long)rows - 256) * 4 / 5));      // rows = 1.25 target + 256
+    const int target = min(cap_target, max(qmin, (int)((float)remaining * frac)));
+    if (remaining <= (unsigned int)target) return 0xffffffffu;
+    const double prob = (double)target / (double)remaining * 0.97;
+    return (unsigned int)(prob * 4294967295.0);
+}
+
+__global__ void select_queries_dev_kernel(int8_t *__restrict__ mask, int T, int H, int W, float frac, int qmin, int rows,
+                                          unsigned int seed, const unsigned int *__restrict__ state,
+                                          long long *__restrict__ qinds, unsigned int *__restrict__ counters) {
+    const unsigned int round = state[0] - 1u;
+    const unsigned int thresh = draw_threshold(counters[0], frac, qmin, rows);
+    const long long n = (long long)T * H * W;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_pad = (n + 31) / 32 * 32;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        bool sel = false;
+        if (i < n && mask[i] != 0) sel = hash3((unsigned)i, (unsigned)(i >> 32) + round, seed) <= thresh;
+        const unsigned int b = __ballot_sync(0xffffffffu, sel);
+        if (b) {
+            const int lane = threadIdx.x & 31;
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&counters[1], __popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (sel) {
+                const unsigned int slot = base + __popc(b & ((1u << lane) - 1));
+                if (slot < (unsigned)rows) {
+                    const int x = (int)(i % W), y = (int)((i / W) % H), t = (int)(i / ((long long)W * H));
+                    qinds[3 * (long long)slot] = t;
+                    qinds[3 * (long long)slot + 1] = y;
+                    qinds[3 * (long long)slot + 2] = x;
+                    mask[i] = 0;
+                }
+            }
+        }
+    }
+}
+
 // rows of qinds beyond the number drawn become invalid queries (t = -1): lets every kernel of a round run
 // with a fixed grid of `cap` rows, so the host never has to wait for the round size
 __global__ void pad_queries_kernel(long long *__restrict__ qinds, const unsigned int *__restrict__ counters, int cap) {
@@ -196,8 +248,9 @@ __device__ __forceinline__ unsigned int row_priority(const long long *q, int H, 
 }
 
 __global__ void round_stamp_kernel(const long long *__restrict__ qinds, const long long *__restrict__ inds, int K,
-                                   unsigned int *__restrict__ owner, unsigned int round_key, unsigned int round, int T,
-                                   int C, int H, int W, int boost) {
+                                   unsigned int *__restrict__ owner, unsigned int round_key, unsigned int round,
+                                   const unsigned int *__restrict__ state, int T, int C, int H, int W, int boost) {
+    if (state) { round = state[0] - 1u; round_key = (65535u - round) << 15; }   // device-controlled round
     const long long *row = inds + (long long)blockIdx.x * K;
     if (!row_valid_block(row, K)) return;
     const unsigned int key = round_key | row_priority(qinds + 3 * (long long)blockIdx.x, H, W, round);
@@ -218,7 +271,9 @@ __global__ void round_stamp_kernel(const long long *__restrict__ qinds, const lo
 
 __global__ void round_drop_kernel(const long long *__restrict__ qinds, long long *__restrict__ inds, int B, int K,
                                   const unsigned int *__restrict__ owner, unsigned int round_key, unsigned int round,
-                                  int8_t *__restrict__ mask, int T, int H, int W, unsigned int *__restrict__ dropped) {
+                                  const unsigned int *__restrict__ state, int8_t *__restrict__ mask, int T, int H, int W,
+                                  unsigned int *__restrict__ dropped) {
+    if (state) { round = state[0] - 1u; round_key = (65535u - round) << 15; }
     const int j = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= B) return;
     const long long *q = qinds + 3 * (long long)j;
@@ -245,10 +300,23 @@ extern "C" int vnlb_round_dedup(const int64_t *qinds, int64_t *inds, int B, int 
     if (B == 0) return VNLB_OK;
     const unsigned int key = (65535u - round) << 15;
     round_stamp_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const long long *)qinds, (const long long *)inds, K, owner, key,
-                                                            round, T, C, H, W, boost);
+                                                            round, nullptr, T, C, H, W, boost);
     round_drop_kernel<<<div_up(B, 8), 256, 0, (cudaStream_t)stream>>>((const long long *)qinds, (long long *)inds, B, K,
-                                                                     owner, key, round, mask, T, H, W, dropped);
+                                                                     owner, key, round, nullptr, mask, T, H, W, dropped);
     return check_launch("vnlb_round_dedup", 2);
+}
+
+extern "C" int vnlb_round_dedup_dev(const int64_t *qinds, int64_t *inds, int B, int K, uint32_t *owner,
+                                    const uint32_t *state, int8_t *mask, int T, int C, int H, int W, int boost,
+                                    uint32_t *dropped, void *stream) {
+    VNLB_REQUIRE(qinds && inds && owner && state && mask && dropped && B >= 0 && K > 0, "vnlb_round_dedup_dev: bad argument");
+    VNLB_REQUIRE(T > 0 && C > 0 && H > 0 && W > 0 && B <= 32768, "vnlb_round_dedup_dev: bad shape");
+    if (B == 0) return VNLB_OK;
+    round_stamp_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const long long *)qinds, (const long long *)inds, K, owner, 0u,
+                                                            0u, state, T, C, H, W, boost);
+    round_drop_kernel<<<div_up(B, 8), 256, 0, (cudaStream_t)stream>>>((const long long *)qinds, (long long *)inds, B, K,
+                                                                     owner, 0u, 0u, state, mask, T, H, W, dropped);
+    return check_launch("vnlb_round_dedup_dev", 2);
 }
 
 extern "C" const char *vnlb_last_error(void) { return g_err; }
@@ -326,6 +394,20 @@ extern "C" int vnlb_pad_queries(int64_t *qinds, const uint32_t *counters, int ca
     VNLB_REQUIRE(qinds && counters && cap > 0, "vnlb_pad_queries: bad argument");
     pad_queries_kernel<<<div_up(cap, 256), 256, 0, (cudaStream_t)stream>>>((long long *)qinds, counters, cap);
     return check_launch("vnlb_pad_queries");
+}
+
+extern "C" int vnlb_round_draw(int8_t *mask, int T, int H, int W, double frac, int qmin, int rows, uint32_t seed,
+                               uint32_t *state, int64_t *qinds, uint32_t *counters, void *stream) {
+    VNLB_REQUIRE(mask && state && qinds && counters && T > 0 && H > 0 && W > 0, "vnlb_round_draw: bad argument");
+    VNLB_REQUIRE(frac > 0.0 && qmin >= 1 && rows >= 1, "vnlb_round_draw: frac > 0, qmin >= 1, rows >= 1");
+    const long long n = (long long)T * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    round_begin_kernel<<<1, 1, 0, st>>>(state, counters);
+    count_mask_kernel<<<grid_for(n, 256), 256, 0, st>>>(mask, n, counters);
+    select_queries_dev_kernel<<<grid_for(n, 256), 256, 0, st>>>(mask, T, H, W, (float)frac, qmin, rows, seed, state,
+                                                               (long long *)qinds, counters);
+    pad_queries_kernel<<<div_up(rows, 256), 256, 0, st>>>((long long *)qinds, counters, rows);
+    return check_launch("vnlb_round_draw", 4);
 }
 
 extern "C" int vnlb_mask_update(int8_t *mask, const int64_t *inds, int B, int K, int T, int C, int H, int W,

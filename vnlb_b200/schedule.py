@@ -69,6 +69,8 @@ class _Workspace:
         ws.ev_copied = [torch.cuda.Event() for _ in range(4)]
         ws.search_stream = torch.cuda.Stream(device=device)
         ws.bayes_stream = torch.cuda.Stream(device=device)
+        ws.graph_stream = torch.cuda.Stream(device=device)      # fast_graph: capture + replay stream
+        ws.round_state = torch.zeros((4,), dtype=torch.int32, device=device)   # device-side round index (vnlb_round_draw)
         ws.dropped = torch.zeros((1,), dtype=torch.int32, device=device)
         ws.counters = torch.zeros((2,), dtype=torch.int32, device=device)
         ws.host = torch.zeros((2,), dtype=torch.int32).pin_memory()
@@ -188,6 +190,101 @@ def _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed
     return nproc - ndrop, nrounds, nmask0, ndrop
 
 
+def _graph_rows(rows_needed, cap):
+    """Rows of a captured round: the smallest of cap, 3/4 cap, 1/2 cap, 3/8 cap, ... (>= 512) that holds the draw."""
+    r = cap
+    while True:
+        for cand in (r * 3 // 4, r // 2):
+            if cand < 512 or cand < rows_needed:
+                return r
+            r = cand
+
+
+def _rounds_graph(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed, est_mask):
+    """The rounds of one step as CUDA-graph replays (args.fast_graph).  A round is a device-controlled program --
+    vnlb_round_draw (count, draw with the probability computed on the device from the live count, pad), search,
+    in-round conflict resolution, mask update, fused Bayes + aggregation -- whose launches depend on no host scalar
+    but the number of rows, so it is captured once per row bucket (_graph_rows: at most ~10 graphs per step) and
+    replayed for every round that fits the bucket: two enqueues per round (the replay and the 8-byte read-back)
+    instead of fifteen launches.  The first round runs eagerly (it allocates what the wrappers allocate lazily: graph
+    capture must not allocate).  The host reads the round size two rounds late, as in _rounds_async, to size the next
+    bucket and to see the mask run empty.  Search and Bayes of consecutive rounds do not overlap in this mode.  The
+    draw uses the live count where the host loop uses a count that is two rounds old: same rule, slightly different
+    draws (both deterministic)."""
+    t, c, h, w = images.shape
+    main = torch.cuda.current_stream()
+    sG = ws.graph_stream
+    dedup = bool(args.get("fast_dedup", FAST_DEFAULTS["fast_dedup"]))
+    owner = torch.full((t, h, w), -1, dtype=torch.int32, device=images.device) if dedup else None
+    ws.dropped.zero_()
+    ws.round_state.zero_()
+    sG.wait_stream(main)
+    copied = ws.ev_copied
+    cnt = ws.counters4[0]
+    qbuf, vbuf, ibuf = ws.qinds2[0], ws.vals2[0], ws.inds2[0]
+    k = int(ibuf.shape[1])
+    remaining = int(est_mask)
+    qmin = min(qmin, max(296, remaining // 64))
+    graphs = {}
+    rows_of = [cap] * 4
+    nproc, nrounds, nmask0 = 0, 0, None
+
+    def enqueue_round(rows):
+        st = L.stream_ptr()
+        qinds, vals, inds = qbuf[:rows], vbuf[:rows], ibuf[:rows]
+        L.check(L.lib.vnlb_round_draw(L.ptr(mask), t, h, w, float(frac), int(qmin), int(rows), seed, L.ptr(ws.round_state),
+                                      L.ptr(qinds), L.ptr(cnt), st), "vnlb_round_draw")
+        search.exec_sim_search_burst(srch_img, qinds, vals, inds, flows, args.sigma, args)
+        if dedup:
+            L.check(L.lib.vnlb_round_dedup_dev(L.ptr(qinds), L.ptr(inds), rows, k, L.ptr(owner), L.ptr(ws.round_state),
+                                               L.ptr(mask), t, c, h, w, int(bool(args.aggreBoost)), L.ptr(ws.dropped), st),
+                    "vnlb_round_dedup_dev")
+        search_mask.update_mask_inds(mask, inds, c, boost=args.aggreBoost)
+        deno.bayes_aggregate_fused(images, inds, args)
+
+    r = 0
+    with torch.cuda.stream(sG):
+        while True:
+            slot = r & 3
+            target = min(cap, max(qmin, int(remaining * frac)))
+            rows = _graph_rows(min(cap, int(target * 1.25) + 256), cap)
+            rows_of[slot] = rows
+            if r == 0:
+                enqueue_round(rows)
+            else:
+                g = graphs.get(rows)
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    g.capture_begin()
+                    try:
+                        enqueue_round(rows)
+                    finally:
+                        g.capture_end()
+                    graphs[rows] = g
+                g.replay()
+            ws.host4[slot].copy_(cnt, non_blocking=True)
+            copied[slot].record(sG)
+            r += 1
+            if r >= 2:
+                old = (r - 2) & 3
+                copied[old].synchronize()
+                rem_old, nsel = int(ws.host4[old][0]), min(int(ws.host4[old][1]), rows_of[old])
+                if nmask0 is None:
+                    nmask0 = rem_old
+                nproc += nsel
+                nrounds += 1
+                if rem_old == 0:
+                    break
+                remaining = max(rem_old - nsel, 1)
+        last = (r - 1) & 3
+        copied[last].synchronize()
+        nproc += min(int(ws.host4[last][1]), rows_of[last])
+    main.wait_stream(sG)
+    ndrop = int(ws.dropped.item()) if dedup else 0
+    del graphs
+    return nproc - ndrop, nrounds, nmask0, ndrop
+
+
 def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None, tile=None, post_fn=None, sync_hook=None):
     """One VNLB step with the throughput schedule (same contract as proc_nl).  `y_range` / `tile`: multi-GPU band of
     reference rows and position of this row tile in the frame (mask.init_mask_device)."""
@@ -217,8 +314,12 @@ def proc_nl_fast(images, flows, args, stats=None, y_range=None, reduce_fn=None, 
         if stats is not None and stats.get("want_row_hist"):
             row_hist = torch.zeros((h,), dtype=torch.float32, device=dev)
             stats["row_hist"] = row_hist
-        nproc, nrounds, nmask0, ndrop = _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed,
-                                                      est + est // 8, row_hist, sync_hook)
+        if args.get("fast_graph", False) and sync_hook is None and row_hist is None and L.timer is None:
+            nproc, nrounds, nmask0, ndrop = _rounds_graph(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed,
+                                                          est + est // 8)
+        else:
+            nproc, nrounds, nmask0, ndrop = _rounds_async(images, flows, args, ws, mask, srch_img, frac, qmin, cap, seed,
+                                                          est + est // 8, row_hist, sync_hook)
         finish_step(images, args, reduce_fn, post_fn)
         if stats is not None:
             stats.setdefault("ndropped", []).append(ndrop)
