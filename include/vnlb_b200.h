@@ -110,10 +110,9 @@ int vnlb_init_mask_tile(int8_t *mask, int T, int H, int W, int ps, int pt, int p
  * (distance, candidate enumeration order t->y->x); slots that cannot be filled
  * (fewer than k candidates) are set to +inf / -1. */
 /* Search kernel selection (A/B measurements and tests; every path returns identical bits): 0 = automatic -- for
- * 7x7x2 patches, a 27x27 window and at most 13 frames the "quad" kernel (4x9 candidates per thread, accumulators in
- * registers over all channel / patch-frame phases), its frame tiles staged by TMA (cp.async.bulk.tensor.3d) when
- * W % 4 == 0 and the image is 16-byte aligned, by 4-byte cp.async otherwise; 1 = never the quad kernel (1-column tiled
- * kernel / generic kernel); 2 = quad kernel without TMA.  Returns the previous setting.
+ * 7x7x2 patches, a 27x27 window and at most 13 frames the "quad" kernel (4x9 candidates per thread, distances in
+ * registers over all channel / patch-frame phases, two-histogram selection), else the 1-column tiled kernel or the
+ * generic kernel; 1 = never the quad kernel; 2 = same as 0.  Returns the previous setting.
  * (Environment: VNLB_SEARCH_PATH at start-up.) */
 int vnlb_set_search_path(int path);
 size_t vnlb_search_workspace_bytes(int Q, const VnlbSearchParams *p);

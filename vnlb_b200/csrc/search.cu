@@ -16,7 +16,6 @@
 //                column of 9 candidates, the query patch lives in registers.
 // Selection: 4-pass radix select on the distance bits in shared memory, tie
 // resolution by enumeration order, bitonic sort of the k survivors.
-#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -619,11 +618,12 @@ search_tiled_kernel(const float *__restrict__ img, int T, int C, int H, int W,
 // the per-candidate accumulation order is exactly the canonical (c, ht, hy, hx) one.  Per phase the thread keeps the
 // 49-value query plane in registers (13 broadcast LDS.128) and slides down 15 tile rows with 2 LDS.128 + 1 LDS.64 each,
 // feeding 4 x 9 accumulators: 58 shared-memory loads per 3528 FSUB/FFMA (the 1-column kernel above: 154 per 882).
-// Tiles are 36 x 33 boxes (row pitch 36 floats, 16-byte aligned quads), one per frame, ALL frames of a phase resident:
-//   * TMA path (W % 4 == 0): one elected thread issues one cp.async.bulk.tensor.3d per frame on the [T*C, H, W]
-//     tensor map of the search image (box start = window corner, any alignment; out-of-frame columns/rows are
-//     zero-filled and only ever read by candidates that are discarded), completion on an mbarrier;
-//   * cp.async path (any W): one warp per tile row, 4-byte copies.
+// Tiles are 36 x 33 boxes (row pitch 36 floats, 16-byte aligned quads), one per frame, ALL frames of a phase resident,
+// staged with 4-byte cp.async (one warp per tile, lane = column).  TMA (cp.async.bulk.tensor) was built and measured
+// first: the instruction needs the box START 16-byte aligned in global memory (x0 % 4 == 0 for float32; any other
+// corner raises an illegal-instruction fault -- tools/experimental/tma_probe.cu), and a window corner is arbitrary;
+// aligning the box instead costs an eighth quad of candidate columns per strip (+11 % FSUB/FFMA issue), more than
+// the 4-byte staging (5 % of the issue slots).
 // Zero flow / rigid trajectory (all frames share one window): frames+1 tiles are staged once per channel and serve
 // both patch frames.  The distances are then written to shared memory (aliasing the tiles) and selected as above.
 // ---------------------------------------------------------------------------
@@ -635,36 +635,6 @@ constexpr int QSLOT = 1204;                // floats per tile slot: 33 * 36 = 11
                                            // frame as the fastest item index, 8 consecutive lanes read 8 different 16-byte bank groups)
 constexpr int QMAXF = 13;                  // frames of the temporal window
 constexpr int QTHREADS = ((QMAXF * QITEMS + 31) / 32) * 32;   // 288
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(a), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "QUAD_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra QUAD_DONE;\n"
-        "bra QUAD_WAIT;\n"
-        "QUAD_DONE:\n"
-        "}\n" ::"r"(a), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_box(float *dst_smem, const CUtensorMap *map, unsigned long long *bar, int x, int y, int z) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(d),
-        "l"(map), "r"(b), "r"(x), "r"(y), "r"(z)
-        : "memory");
-}
 
 // one (channel, patch frame) plane of one item: 36 candidates x 49 terms.  The loop over the patch row hy is NOT
 // unrolled: its body (9 tile rows x 56 FSUB/FFMA pairs + 29 shared-memory loads, 8.5 KB of code) stays in the
@@ -907,23 +877,16 @@ __device__ bool select_topk_regs(SearchShared &S, const float (&acc)[QROWS * QCO
     return true;
 }
 
-template <bool USE_TMA>
 __global__ void __launch_bounds__(QTHREADS, 2)
-search_quad_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ img, int T, int C, int H, int W,
+search_quad_kernel(const float *__restrict__ img, int T, int C, int H, int W,
                    const long long *__restrict__ qinds, const float *__restrict__ fflow,
                    const float *__restrict__ bflow, VnlbSearchParams p, int P, int ncand_max,
                    float *__restrict__ vals, long long *__restrict__ inds) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SearchShared &S = *reinterpret_cast<SearchShared *>(smem_raw);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(SearchShared));
-    unsigned long long *mbar = keys + P;
-    float *qpatch = reinterpret_cast<float *>(mbar + 2);   // [dist_chnls][TPT][7][8]
-    float *tiles;
-    {
-        unsigned char *tb = reinterpret_cast<unsigned char *>(qpatch + p.dist_chnls * TPT * 56);
-        const unsigned sa = (unsigned)__cvta_generic_to_shared(tb);
-        tiles = reinterpret_cast<float *>(tb + ((128u - (sa & 127u)) & 127u));   // TMA destinations: 128-byte aligned
-    }
+    float *qpatch = reinterpret_cast<float *>(keys + P);   // [dist_chnls][TPT][7][8]
+    float *tiles = qpatch + p.dist_chnls * TPT * 56;       // 16-byte aligned (56 floats per plane)
     float *dist = tiles;                                    // after the last phase
 
     const int q = blockIdx.x, tid = threadIdx.x;
@@ -941,7 +904,6 @@ search_quad_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
     const long long HW = (long long)H * W, CHW = (long long)C * HW;
     const int dc = p.dist_chnls;
     if (tid < 32) build_windows_warp(S, t0, y0, x0, T, H, W, fflow, bflow, p);
-    if (USE_TMA && tid == 0) mbar_init(mbar, 1);
     for (int i = tid; i < dc * TPT * 49; i += blockDim.x) {
         const int pl = i / 49, r = i - pl * 49, c = pl / TPT, ht = pl - c * TPT, hy = r / 7, hx = r - hy * 7;
         qpatch[pl * 56 + hy * 8 + hx] = img[(long long)(t0 + ht) * CHW + c * HW + (long long)(y0 + hy) * W + x0 + hx];
@@ -956,7 +918,6 @@ search_quad_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
     float acc[QROWS * QCOLS];
 #pragma unroll
     for (int i = 0; i < QROWS * QCOLS; ++i) acc[i] = 0.f;
-    unsigned parity = 0;
     const int nslots = sw ? nfr + 1 : nfr;
     // one loop over the (channel, patch frame) phases; with a shared window the tiles staged for patch frame 0 also
     // serve patch frame 1 (slot f + 1)
@@ -965,19 +926,7 @@ search_quad_kernel(const __grid_constant__ CUtensorMap tmap, const float *__rest
         const int c = ph >> 1, ht = ph & 1;
         if (!sw || ht == 0) {
             __syncthreads();                 // every thread is done reading the tiles of the previous phase
-            if (USE_TMA) {
-                if (tid == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                    mbar_expect_tx(mbar, (unsigned)(nslots * QTH * QTW * 4));
-                    for (int sl = 0; sl < nslots; ++sl) {
-                        const FrameWin w = S.fw[sw ? 0 : sl];
-                        const int tt = sw ? w.t + sl : w.t + ht;
-                        tma_load_box(tiles + sl * QSLOT, &tmap, mbar, w.x0, w.y0, tt * C + c);
-                    }
-                }
-                mbar_wait(mbar, parity);
-                parity ^= 1u;
-            } else {
+            {
                 // one warp per tile slot: lane = column for columns 0..31 (one copy per row and lane, two pointer
                 // increments per row), then lane = row for column 32
                 const int lane = tid & 31, wrp = tid >> 5, nw = blockDim.x >> 5;
@@ -1058,9 +1007,8 @@ static int next_pow2(int v) {
 
 static bool tiled_ok(const VnlbSearchParams *p) { return p->ps == TPS && p->pt == TPT && p->w_s == TWS; }
 
-// search path: 0 = automatic (quad kernel with TMA staging when the image allows it, quad kernel with cp.async
-// staging otherwise, 1-column tiled kernel beyond 13 frames, generic kernel for other shapes), 1 = never the quad
-// kernel, 2 = quad kernel without TMA
+// search path: 0 / 2 = automatic (quad kernel for 7x7x2 patches, a 27x27 window and at most 13 frames, 1-column tiled
+// kernel beyond 13 frames, generic kernel for other shapes), 1 = never the quad kernel
 static int g_search_path = -1;
 static int search_path() {
     if (g_search_path < 0) {
@@ -1069,40 +1017,6 @@ static int search_path() {
         if (g_search_path < 0 || g_search_path > 2) g_search_path = 0;
     }
     return g_search_path;
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        void *f = nullptr;
-        cudaDriverEntryPointQueryResult qr;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
-            qr == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)f;
-        (void)cudaGetLastError();
-        tried = true;
-    }
-    return fn;
-}
-
-// tensor map of the search image as [T*C, H, W] float32 with a 36 x 33 x 1 box; false if the image cannot be described
-// (row pitch or base not 16-byte aligned, frame smaller than a box, no driver entry point)
-static bool make_tile_map(CUtensorMap *map, const float *img, int T, int C, int H, int W) {
-    if ((W & 3) || (reinterpret_cast<uintptr_t>(img) & 15) || W < QTW || H < QTH) return false;
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) return false;
-    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)T * (cuuint64_t)C};
-    const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * (cuuint64_t)H * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)QTW, (cuuint32_t)QTH, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(img), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace vnlb
@@ -1146,29 +1060,16 @@ extern "C" int vnlb_search_topk(const float *img, int T, int C, int H, int W, co
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
     if (quad) {
-        // [SearchShared][keys][mbarrier][query planes][<=127 B of alignment][frames+1 tile slots; later the distances]
+        // [SearchShared][keys][query planes][frames+1 tile slots; after the last phase the distances + candidate list]
         const size_t tile_bytes = (size_t)(nfr + 1) * QSLOT * 4;
         const size_t sel_bytes = (((size_t)ncand_max + 1) / 2 + kKeyCap) * 8;   // distances (fallback) + candidate list
-        const size_t smem = sizeof(SearchShared) + (size_t)P * 8 + 16 + (size_t)p->dist_chnls * TPT * 56 * 4 + 128 +
+        const size_t smem = sizeof(SearchShared) + (size_t)P * 8 + (size_t)p->dist_chnls * TPT * 56 * 4 +
                             (tile_bytes > sel_bytes ? tile_bytes : sel_bytes);
         const int threads = ((nfr * QITEMS + 31) / 32) * 32;
-        CUtensorMap map;
-        memset(&map, 0, sizeof(map));
-        // TMA needs the box start 16-byte aligned in global memory (x0 % 4 == 0; measured with
-        // tools/experimental/tma_probe.cu: any other corner raises an illegal-instruction fault), which an arbitrary
-        // window corner is not: the TMA instantiation is kept for aligned-only use and is off
-        const bool tma = false && search_path() == 0 && make_tile_map(&map, img, T, C, H, W);
-        if (tma) {
-            e = cudaFuncSetAttribute(search_quad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("vnlb_search_topk: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
-            search_quad_kernel<true><<<Q, threads, smem, st>>>(map, img, T, C, H, W, (const long long *)qinds, fflow, bflow,
-                                                              *p, P, ncand_max, vals, (long long *)inds);
-        } else {
-            e = cudaFuncSetAttribute(search_quad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("vnlb_search_topk: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
-            search_quad_kernel<false><<<Q, threads, smem, st>>>(map, img, T, C, H, W, (const long long *)qinds, fflow, bflow,
-                                                               *p, P, ncand_max, vals, (long long *)inds);
-        }
+        e = cudaFuncSetAttribute(search_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("vnlb_search_topk: %s", cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
+        search_quad_kernel<<<Q, threads, smem, st>>>(img, T, C, H, W, (const long long *)qinds, fflow, bflow, *p, P,
+                                                    ncand_max, vals, (long long *)inds);
         return check_launch("vnlb_search_topk");
     }
     size_t smem = sizeof(SearchShared) + (size_t)P * 8 + (size_t)ncand_max * 4;
