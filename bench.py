@@ -432,16 +432,20 @@ def single_gpu_extras(vnlb_b200, device, fp32_peak, hbm_peak, psnr_delta, args):
     try:
         torch.cuda.synchronize()
         evs[0].record()
-        for _ in range(n2):
+        per_call = [torch.cuda.Event(enable_timing=True) for _ in range(n2)]
+        for i2 in range(n2):
             st = {}
             d2, b2, _ = vnlb_b200.denoise(noisy2, c2["sigma"], gpuid=device.index, verbose=False, stats=st)
+            per_call[i2].record()
         evs[1].record()
         torch.cuda.synchronize()
     finally:
         gc.enable()
+    per_call_ms = [round((evs[0] if i2 == 0 else per_call[i2 - 1]).elapsed_time(per_call[i2]), 1) for i2 in range(n2)]
     ms2 = evs[0].elapsed_time(evs[1]) / n2
     extras["config2"] = dict(workload="854x480x20 synthetic RGB, sigma=20, no flow (BASELINE configs[1])",
                              value=c2["T"] * c2["H"] * c2["W"] / 1e6 / (ms2 / 1e3), unit="Mpx/s", ms_per_step=ms2, steps=n2,
+                             per_call_ms=per_call_ms,
                              groups_per_step=st["ngroups"], dropped_per_step=st.get("ndropped"),
                              psnr=dict(basic=psnr_of(b2, clean2), deno=psnr_of(d2, clean2)))
     del noisy2, d2, b2

@@ -265,6 +265,21 @@ class BandRebalancer:
             mask[:, lo - ya:hi - ya] = buf
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One side stream per device for the whole process.  torch's caching allocator keeps a pool per stream: a stream
+    created per call made every call's gather buffers (1.7 GB at 1080p x 30) come from fresh cudaMallocs -- reserved
+    memory grew call after call and the cudaMalloc (peer mappings under NCCL) stalled the host for 100-350 ms at
+    random (tools/dist_probe.py)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 # ------------------------------------------------------------------------------------------------ inputs
 def _rows_to_device(x, ya, yb, device):
     """Rows [ya, yb) of a [T,C,H,W] host (numpy / torch, ideally pinned) or device array as a contiguous float32 device
@@ -375,7 +390,7 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
 
         noisy_yuv = color.rgb2yuv(noisy_t)
         tile = (ya, H)
-        side = torch.cuda.Stream(device=device) if gather else None
+        side = _side_stream(device) if gather else None
         outs = []
         basic_yuv = None
         for step in (0, 1):
