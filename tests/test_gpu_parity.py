@@ -147,7 +147,8 @@ SEARCH_CASES = [
 
 
 @pytest.mark.parametrize("shape,step,over", SEARCH_CASES)
-def test_search_bit_exact(vb, shape, step, over):
+def test_search_bit_exact_vs_oracle(vb, shape, step, over):
+    """Parity against OUR oracle (oracle/vnlb_oracle.c): the reference's search lives in the absent vpss package."""
     T, C, H, W = shape
     rs = np.random.RandomState(10)
     img = (rs.rand(T, C, H, W) * 255).astype(np.float32)
@@ -165,7 +166,7 @@ def test_search_bit_exact(vb, shape, step, over):
     assert np.all(gi[q.shape[0]:] == -1)
 
 
-def test_search_with_flows_bit_exact(vb):
+def test_search_with_flows_bit_exact_vs_oracle(vb):
     T, C, H, W = 9, 3, 56, 72
     rs = np.random.RandomState(11)
     img = (rs.rand(T, C, H, W) * 255).astype(np.float32)

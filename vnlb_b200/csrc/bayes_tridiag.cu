@@ -724,27 +724,32 @@ __device__ __forceinline__ void tridiag_regs2(float2 (&bl)[2 * ((NR + 3) / 4)], 
 // and, every fourth step, the new window chunk from the warp that owns it.  Same arithmetic per element as
 // tridiag_regs2; only the grouping of the mat-vec partial sums differs.
 // Shared scratch (floats): xs[VL] vs[VL] ws[VL] part[4][NR] win[NR][4] d[KN] e[KN] tau[KN] reflectors.
+// -------------------------------------------------------------- P1. tridiag_cols (column-split elimination)
 template <int QDG, int NR, int CEND> __host__ __device__ constexpr int tridiag_cols_scratch_floats() {
-    return 3 * (NR + 4) + 8 * NR + 3 * ((QDG - 1 - CEND - (QDG - NR) + 1 + 3) & ~3) +
+    return 6 * (NR + 4) + 8 * NR + 8 + 3 * ((NR - CEND + 3) & ~3) +
            ((refl_off(QDG, QDG - CEND) - refl_off(QDG, QDG - NR) + 3) & ~3);
 }
 
+// Second version: a warp keeps the per-row state (x, r, window) only of the row slot it PUBLISHES (warp h < 3: rows
+// l + 32 h); everything another warp needs of a row comes from shared memory -- v_i, w_i of its own rows for the sweep
+// (6 loads), the scalars of rows c, c-1, c-2 (broadcast loads of part / xs / rs), and x~^T B x~ as the sum of the four
+// warps' partial sums (each warp dots ITS partial mat-vec with the next x during the sweep).  xs / rs are ping-pong
+// buffers: a step reads the current column while the publishers write the next one.
 template <int QDG, int NR, int CEND, int OPITCH, int OREFL>
 __device__ __forceinline__ void tridiag_cols(const float *Bm, int ldb, float *sv, float *out, float *trail, int lane, int h) {
     constexpr int NS = NR / 32, NCH = NR / 4, NL = NCH / 4, VL = NR + 4;
     constexpr int K0 = QDG - NR, K1 = QDG - 1 - CEND;
     constexpr int KN = (K1 - K0 + 1 + 3) & ~3;
     constexpr int R0 = refl_off(QDG, K0), R1 = refl_off(QDG, K1 + 1);
-    constexpr unsigned FULL = 0xffffffffu;
     static_assert(NS == 3 && NCH % 4 == 0 && CEND % 32 == 0 && CEND >= 32 && CEND < NR, "tridiag_cols: 96 rows in three slots, 4 warps");
-    float *xs = sv, *vs = sv + VL, *ws = sv + 2 * VL, *part = sv + 3 * VL, *win = part + 4 * NR;
-    float *sd = win + 4 * NR, *se = sd + KN, *st = se + KN, *srf = st + KN;
-    const uint32_t aX = smem_u32(xs), aV = smem_u32(vs), aW = smem_u32(ws);
+    float *xs0 = sv, *rs0 = sv + 2 * VL, *vs = sv + 4 * VL, *ws = sv + 5 * VL, *part = sv + 6 * VL, *win = part + 4 * NR;
+    float *xbx = win + 4 * NR;                     // [0..3] partial x~^T B x~ per warp, [4] the next diagonal entry
+    float *sd = xbx + 8, *se = sd + KN, *st = se + KN, *srf = st + KN;
+    const uint32_t aV = smem_u32(vs), aW = smem_u32(ws);
     int row[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) row[s] = lane + 32 * s;
-    // this lane's rows, this warp's column chunks
-    float2 b[NS][2 * NL];
+    float2 b[NS][2 * NL];                          // this lane's rows, this warp's column chunks
 #pragma unroll
     for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -753,30 +758,41 @@ __device__ __forceinline__ void tridiag_cols(const float *Bm, int ldb, float *sv
             b[s][2 * t] = make_float2(f.x, f.y);
             b[s][2 * t + 1] = make_float2(f.z, f.w);
         }
-    auto from_row = [&](int r, const float (&a)[NS]) -> float {
-        const int sl = r >> 5;
-        return __shfl_sync(FULL, sl == 0 ? a[0] : (sl == 1 ? a[1] : a[2]), r & 31);
-    };
+    const bool own = h < NS;                       // warps 0..2 publish row slot h; warp 3 writes d, e, tau
+    const int io = lane + 32 * (own ? h : 0);
     constexpr int c0 = NR - 1;
-    float x[NS], r[NS], y[NS], wq[NS][4];
     int Iw = (c0 - 2) >> 2;
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const float x0 = Bm[row[s] * ldb + c0];
-        r[s] = Bm[row[s] * ldb + c0 - 1];
-        x[s] = row[s] < c0 ? x0 : 0.f;
-        const float4 f = *reinterpret_cast<const float4 *>(Bm + row[s] * ldb + 4 * Iw);
-        wq[s][0] = f.x; wq[s][1] = f.y; wq[s][2] = f.z; wq[s][3] = f.w;
+    float x = 0.f, r = 0.f, wq0 = 0.f, wq1 = 0.f, wq2 = 0.f, wq3 = 0.f;
+    if (own) {
+        const float x0 = Bm[io * ldb + c0];
+        r = Bm[io * ldb + c0 - 1];
+        x = io < c0 ? x0 : 0.f;
+        const float4 f = *reinterpret_cast<const float4 *>(Bm + io * ldb + 4 * Iw);
+        wq0 = f.x; wq1 = f.y; wq2 = f.z; wq3 = f.w;
     }
-    float dk = Bm[c0 * ldb + c0];
-    for (int j = 32 * h + lane; j < 3 * VL; j += 128) sv[j] = 0.f;
+    const float dk0 = Bm[c0 * ldb + c0];
+    for (int j = 32 * h + lane; j < 6 * VL; j += 128) sv[j] = 0.f;
     __syncthreads();
-    if (h < NS) xs[row[h]] = x[h];
+    if (own) { xs0[io] = x; rs0[io] = r; }
+    if (h == 3 && lane == 0) xbx[4] = dk0;
     __syncthreads();
-    {   // partial y = B x over this warp's chunks, every row slot
+    // partial mat-vec of this warp's chunks for every row slot + its share of x~^T B x~
+    auto sweep_tail = [&](const float2 (&acc)[NS][2], const float *xcur) {
+        float dot = 0.f;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float ps = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
+            part[4 * row[s] + h] = ps;
+            dot = fmaf(xcur[row[s]], ps, dot);
+        }
+        dot = warp_sum(dot);
+        if (lane == 0) xbx[h] = dot;
+    };
+    {
         float2 acc[NS][2];
 #pragma unroll
         for (int s = 0; s < NS; ++s) acc[s][0] = acc[s][1] = make_float2(0.f, 0.f);
+        const uint32_t aX = smem_u32(xs0);
 #pragma unroll
         for (int t = 0; t < NL; ++t) {
             const float4 x4 = lds128(aX + 16 * (4 * t + h));
@@ -786,28 +802,27 @@ __device__ __forceinline__ void tridiag_cols(const float *Bm, int ldb, float *sv
                 acc[s][1] = __ffma2_rn(b[s][2 * t + 1], make_float2(x4.z, x4.w), acc[s][1]);
             }
         }
-#pragma unroll
-        for (int s = 0; s < NS; ++s) part[h * NR + row[s]] = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
+        sweep_tail(acc, xs0);
     }
     bool winload = false;
+    int pp = 0;
     for (int c = NR - 1; c >= CEND; --c) {
         const int k = NR - 1 - c;
+        const float *xc = xs0 + pp * VL, *rc = rs0 + pp * VL;
+        float *xn_s = xs0 + (pp ^ 1) * VL, *rn_s = rs0 + (pp ^ 1) * VL;
         __syncthreads();                                                       // B1: partial sums (and a new window) are published
         if (winload) {
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const float4 f = *reinterpret_cast<const float4 *>(win + 4 * row[s]);
-                wq[s][0] = f.x; wq[s][1] = f.y; wq[s][2] = f.z; wq[s][3] = f.w;
-            }
+            if (own) { const float4 f = *reinterpret_cast<const float4 *>(win + 4 * io); wq0 = f.x; wq1 = f.y; wq2 = f.z; wq3 = f.w; }
             winload = false;
         }
-#pragma unroll
-        for (int s = 0; s < NS; ++s)
-            y[s] = (part[row[s]] + part[NR + row[s]]) + (part[2 * NR + row[s]] + part[3 * NR + row[s]]);
-        const float xBx = warp_sum(fmaf(x[2], y[2], fmaf(x[1], y[1], x[0] * y[0])));   // x = 0 on rows >= c
-        const float yc = from_row(c, y), ycm1 = from_row(c - 1, y), ycm2 = from_row(c - 2, y);
-        const float alpha = from_row(c - 1, x), bcc = from_row(c - 1, r);
-        const float xcm2 = from_row(c - 2, x), rcm2 = from_row(c - 2, r);
+        const float4 pc = *reinterpret_cast<const float4 *>(part + 4 * c);
+        const float4 pc1 = *reinterpret_cast<const float4 *>(part + 4 * (c - 1));
+        const float4 pc2 = *reinterpret_cast<const float4 *>(part + 4 * (c - 2));
+        const float4 xb = *reinterpret_cast<const float4 *>(xbx);
+        const float yc = (pc.x + pc.y) + (pc.z + pc.w), ycm1 = (pc1.x + pc1.y) + (pc1.z + pc1.w), ycm2 = (pc2.x + pc2.y) + (pc2.z + pc2.w);
+        const float xBx = (xb.x + xb.y) + (xb.z + xb.w);
+        const float alpha = xc[c - 1], xcm2 = xc[c - 2], bcc = rc[c - 1], rcm2 = rc[c - 2];
+        const float dk = xbx[4];
         const float a2 = alpha * alpha;
         const float nrm2 = fmaxf(yc, a2);
         const bool skip = (nrm2 == a2);
@@ -823,41 +838,39 @@ __device__ __forceinline__ void tridiag_cols(const float *Bm, int ldb, float *sv
         const float wcm1 = fmaf(-hs, 1.f, ts * fmaf(-beta, bcc, ycm1));
         const float vcm2 = xcm2 * scale;
         const float wcm2 = fmaf(-hs, vcm2, ts * fmaf(-beta, rcm2, ycm2));
-        const int wsel = (c - 2) & 3;
-        float v[NS], w[NS], xn[NS], rn[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const bool act = row[s] < c;
-            v[s] = (row[s] == c - 1) ? 1.f : x[s] * scale;
-            w[s] = fmaf(-hs, v[s], ts * fmaf(-beta, r[s], y[s]));
-            if (!act) { v[s] = 0.f; w[s] = 0.f; }                              // dead rows: the update is a no-op
-            const float q = wsel == 0 ? wq[s][0] : (wsel == 1 ? wq[s][1] : (wsel == 2 ? wq[s][2] : wq[s][3]));
-            xn[s] = fmaf(-v[s], wcm1, fmaf(-w[s], 1.f, r[s]));
-            rn[s] = fmaf(-v[s], wcm2, fmaf(-w[s], vcm2, q));
+        float vo = 0.f, wo = 0.f, xno = 0.f, rno = 0.f;
+        if (own) {                                                             // this warp's row slot: v, w, next x and r
+            const float4 po = *reinterpret_cast<const float4 *>(part + 4 * io);
+            const float y = (po.x + po.y) + (po.z + po.w);
+            const bool act = io < c;
+            vo = (io == c - 1) ? 1.f : x * scale;
+            wo = fmaf(-hs, vo, ts * fmaf(-beta, r, y));
+            if (!act) { vo = 0.f; wo = 0.f; }                                  // dead rows: the update is a no-op
+            const int wsel = (c - 2) & 3;
+            const float q = wsel == 0 ? wq0 : (wsel == 1 ? wq1 : (wsel == 2 ? wq2 : wq3));
+            xno = fmaf(-vo, wcm1, fmaf(-wo, 1.f, r));
+            rno = fmaf(-vo, wcm2, fmaf(-wo, vcm2, q));
+            vs[io] = vo;
+            ws[io] = wo;
+            if (act) srf[refl_off(QDG, K0 + k) - R0 + (c - 1 - io)] = vo;
+            xn_s[io] = (io < c - 1) ? xno : 0.f;
+            rn_s[io] = rno;
+            if (io == c - 1) xbx[5] = xno;                                     // B[c-1][c-1] after the update: the next diagonal entry
+        } else if (lane == 0) {
+            sd[k] = dk; se[k] = beta; st[k] = tau;
         }
-        if (h < NS) {                                                          // warp h publishes row slot h
-            const float pv = h == 0 ? v[0] : (h == 1 ? v[1] : v[2]), pw = h == 0 ? w[0] : (h == 1 ? w[1] : w[2]);
-            const float pxn = h == 0 ? xn[0] : (h == 1 ? xn[1] : xn[2]);
-            const int i = lane + 32 * h;
-            if (i < c) {
-                vs[i] = pv;
-                ws[i] = pw;
-                srf[refl_off(QDG, K0 + k) - R0 + (c - 1 - i)] = pv;
-                xs[i] = (i < c - 1) ? pxn : 0.f;
-            }
-            if (i == c) xs[i] = 0.f;
-        }
-        if (h == 3 && lane == 0) { sd[k] = dk; se[k] = beta; st[k] = tau; }
-        dk = from_row(c - 1, xn);                                              // B[c-1][c-1] after the update
-        __syncthreads();                                                       // B2: v, w and the next x are published
+        __syncthreads();                                                       // B2: v, w and the next x / r are published
+        if (h == 3 && lane == 0) xbx[4] = xbx[5];
         {
             float2 nv[NS], nw[NS], acc[NS][2];
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                nv[s] = make_float2(-v[s], -v[s]);
-                nw[s] = make_float2(-w[s], -w[s]);
+                const float v_s = vs[row[s]], w_s = ws[row[s]];
+                nv[s] = make_float2(-v_s, -v_s);
+                nw[s] = make_float2(-w_s, -w_s);
                 acc[s][0] = acc[s][1] = make_float2(0.f, 0.f);
             }
+            const uint32_t aX = smem_u32(xn_s);
             const int nlive = (c + 3) >> 2;                                    // chunks holding a column < c
             const int tl = nlive > h ? (nlive - h + 3) >> 2 : 0;               // ... of this warp
 #define VNLB_C1(T)                                                                       \
@@ -886,16 +899,12 @@ __device__ __forceinline__ void tridiag_cols(const float *Bm, int ldb, float *sv
                 default: break;
             }
 #undef VNLB_C1
-            {   // the window copies get the same update
+            if (own) {   // the window copy of this warp's row slot gets the same update
                 const float4 v4 = lds128(aV + 16 * Iw), w4 = lds128(aW + 16 * Iw);
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    wq[s][0] = fmaf(-v[s], w4.x, fmaf(-w[s], v4.x, wq[s][0])); wq[s][1] = fmaf(-v[s], w4.y, fmaf(-w[s], v4.y, wq[s][1]));
-                    wq[s][2] = fmaf(-v[s], w4.z, fmaf(-w[s], v4.z, wq[s][2])); wq[s][3] = fmaf(-v[s], w4.w, fmaf(-w[s], v4.w, wq[s][3]));
-                }
+                wq0 = fmaf(-vo, w4.x, fmaf(-wo, v4.x, wq0)); wq1 = fmaf(-vo, w4.y, fmaf(-wo, v4.y, wq1));
+                wq2 = fmaf(-vo, w4.z, fmaf(-wo, v4.z, wq2)); wq3 = fmaf(-vo, w4.w, fmaf(-wo, v4.w, wq3));
             }
-#pragma unroll
-            for (int s = 0; s < NS; ++s) part[h * NR + row[s]] = (acc[s][0].x + acc[s][0].y) + (acc[s][1].x + acc[s][1].y);
+            sweep_tail(acc, xn_s);
         }
         if (((c - 3) >> 2) != Iw) {                                            // next step needs column c-3: its owner publishes the chunk
             Iw = (c - 3) >> 2;
@@ -910,11 +919,11 @@ __device__ __forceinline__ void tridiag_cols(const float *Bm, int ldb, float *sv
             }
             winload = true;
         }
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            x[s] = (row[s] < c - 1) ? xn[s] : 0.f;
-            r[s] = rn[s];
+        if (own) {
+            x = (io < c - 1) ? xno : 0.f;
+            r = rno;
         }
+        pp ^= 1;
     }
     {   // trailing CEND x CEND matrix for the next phase: row i at trail + i * CEND
 #pragma unroll
@@ -935,6 +944,7 @@ __device__ __forceinline__ void tridiag_cols(const float *Bm, int ldb, float *sv
     for (int idx = tid; idx < R1 - R0; idx += 128) out[OREFL + R0 + idx] = srf[idx];
 }
 
+// -------------------------------------------------------------- P2. tridiag_head_smem (first two steps)
 // The first QDG - NR Householder steps on the symmetric matrix M (shared memory, pitch ld, index-reversed like
 // everywhere here): plain three-pass steps (v; p = M v; rank-2 update), one thread per row -- two steps of 98 before
 // tridiag_cols takes the 96 x 96 rest.  Same d / e / tau / reflector conventions as tridiag_regs.
@@ -999,6 +1009,7 @@ __device__ __forceinline__ void tridiag_head_smem(float *M, int ld, float *scr, 
     }
 }
 
+// -------------------------------------------------------------- P3. kernels of the split path
 // Workspace per problem (floats): d[LDG] e[LDG] tau[LDG] mean[LDG] reflectors[nref] trailing matrix[NR2 x NR2];
 // tau[LDG-1] doubles as the "problem is valid" flag between the kernels of the split path.
 constexpr int SPLIT_NR2 = 64;                      // trailing size handed from phase 1 to phase 2
@@ -1230,6 +1241,7 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
     int co[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) co[q] = col_off(min(lane + 32 * q, QD - 1));
+    // -------------------------------------------------------------- P4. cov4: stage the patches
     // ---- stage all n patches (every load independent: one exposed latency)
     constexpr int SU = 5;                            // patches in flight per warp (20 independent loads per lane)
     for (int n0 = warp; n0 < n; n0 += SU * (TT / 32)) {
@@ -1255,6 +1267,7 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
         }
     }
     __syncthreads();
+    // -------------------------------------------------------------- P5. cov4: centre
     // ---- centre (same summation order as bayes_kernel: 4 interleaved partial sums)
     const float inv_n = 1.f / (float)n;
     if (tid < LDQ) {
@@ -1270,6 +1283,7 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
         if (tid < QD) wsp[3 * LDQ + (QD - 1 - tid)] = mj; else wsp[3 * LDQ + tid] = 0.f;
     }
     __syncthreads();
+    // -------------------------------------------------------------- P6. cov4: covariance tiles + mirror
     // ---- covariance: 8 x 8 register tiles of the lower triangle, accumulated over the patches in order (entries
     //      bit-identical to bayes_kernel).  The kernel is bound by the shared-memory data pipe (ncu: 73-79 % busy), so the
     //      covariance is formed where a loaded operand feeds most FMAs (4 LDS.128 per 32 FFMA2), then mirrored through
@@ -1331,6 +1345,7 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
         }
     }
     __syncthreads();
+    // -------------------------------------------------------------- P7. cov4: trace, then the elimination calls
     float dg = (tid < QD) ? Y[tid * LDQ + tid] : 0.f;   // diagonal entry (already divided by n)
     if (a.dbg_mat) {                                 // parity hook: the covariance in natural (un-reversed) index order
         float *o = a.dbg_mat + (size_t)blockIdx.x * QD * QD;
@@ -1351,6 +1366,7 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
     tridiag_cols<QD, COLS_NR, SPLIT_NR2, LDQ, 4 * LDQ>(Y, LDQ, sv, wsp, wsp + split_trail_off<QD>(), lane, warp);
 }
 
+// -------------------------------------------------------------- P8. later kernels
 // Split path, later phases of the tridiagonalisation: the NR x NR trailing matrix comes from the workspace (float
 // offset TIN, row pitch NR), columns NR-1 .. CEND are eliminated by NT = round32(NR) threads, and unless CEND == 2 the
 // CEND x CEND rest goes back to the workspace at TOUT.  Registers ~ NR + 62: 64 threads x 126 registers => 8 CTAs per SM
@@ -2541,11 +2557,10 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         // bound by FFMA2 / LDS throughput, not by occupancy (profiles/r1_summary.md).
         constexpr int NCHQ = (QD + 3) / 4;
         size_t smem1 = (size_t)(ybody + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
-        // VNLB_COV4=1: elimination 98 -> 64 with the columns split over the warps (cov_tridiag4_kernel).  Parity-green and
-        // 12 x less shared-memory traffic per FMA in the sweep, but the per-row scalar work is replicated in every warp
-        // (5.1e8 vs 4.0e8 warp instructions per 2048 groups): 14.58 vs 14.74 ms per 16384 groups, i.e. within 1 % of
-        // tridiag_regs (profiles/r2_summary.md).  Off by default.
-        static const int cols4 = []() { const char *e4 = getenv("VNLB_COV4"); return (e4 && e4[0] == '1') ? 1 : 0; }();
+        // Elimination 98 -> 64 with the columns split over the warps (cov_tridiag4_kernel: 12 x less shared-memory traffic per
+        // FMA in the sweep, 128 registers, 4 CTAs per SM): 14.44 vs 14.73 ms per 16384 groups (profiles/r2_summary.md).
+        // VNLB_COV4=0 selects tridiag_regs (one row per thread) for A/B measurements.
+        static const int cols4 = []() { const char *e4 = getenv("VNLB_COV4"); return (e4 && e4[0] == '0') ? 0 : 1; }();
         const size_t smem1_4 = (size_t)(yrows * 100 + tridiag_cols_scratch_floats<QD, COLS_NR, SPLIT_NR2>() + 8 + ((a.L.n + 3) & ~3) + 4) * sizeof(float);
         auto k1 = cols4 ? cov_tridiag4_kernel<FUSED, QD> : cov_tridiag_kernel<FUSED, QD, NCHQ>;
         if (cols4) smem1 = smem1_4;
