@@ -2116,6 +2116,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 const int mid = qd >> 1;
                 if (fwd) {
                     float best = fabsf(z[qd - 1]);
+#pragma unroll 4
                     for (int i = qd - 2; i >= mid; --i) {
                         const float gam = fabsf(z[i] + zb[i] - (d[i] - l));
                         if (gam < best) { best = gam; r = i; }
@@ -2124,6 +2125,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 } else if (bwd) {
                     float best = 3.4e38f;
                     r = 0;
+#pragma unroll 4
                     for (int i = mid - 1; i >= 0; --i) {
                         const float gam = fabsf(z[i] + zb[i] - (d[i] - l));
                         if (gam < best) { best = gam; r = i; }
@@ -2135,8 +2137,9 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 if (fwd) {                                 // z_r = 1; upwards with D+
                     float zi = 1.f;
                     nrm = 1.f;
-                    for (int i = r - 1; i >= 0; --i) {
-                        zi = -(e[i] / z[i]) * zi;
+#pragma unroll 4
+                    for (int i = r - 1; i >= 0; --i) {   // (the ratio does not depend on zi: loads and divisions of 4 iterations overlap)
+                        zi = -__fdividef(e[i], z[i]) * zi;
                         z[i] = zi;
                         nrm = fmaf(zi, zi, nrm);
                     }
@@ -2144,8 +2147,9 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                     blo[ev] = nrm;
                 } else if (bwd) {                          // downwards with D-
                     float zi = 1.f;
+#pragma unroll 4
                     for (int i = r; i < qd - 1; ++i) {
-                        zi = -(e[i] / zb[i + 1]) * zi;
+                        zi = -__fdividef(e[i], zb[i + 1]) * zi;
                         z[i + 1] = zi;
                         nrm = fmaf(zi, zi, nrm);
                     }
@@ -2157,6 +2161,7 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                     const float sc = rsqrtf(nrm);
                     const int i0 = fwd ? 0 : r + 1, i1 = fwd ? r + 1 : qd;
                     if (nrm < 3.0e38f && sc > 0.f) {
+#pragma unroll 4
                         for (int i = i0; i < i1; ++i) z[i] *= sc;
                     } else {                             // overflow guard (never seen): fall back to the twist basis vector
                         for (int i = i0; i < i1; ++i) z[i] = (i == r) ? 1.f : 0.f;
@@ -2194,20 +2199,23 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                     z[i] = dm;
                 }
                 float zi = 1.f, nrm = 1.f;                 // z_r = 1; upwards with D+, downwards with D-
+#pragma unroll 4
                 for (int i = r - 1; i >= 0; --i) {
-                    zi = -(e[i] / z[i]) * zi;
+                    zi = -__fdividef(e[i], z[i]) * zi;
                     z[i] = zi;
                     nrm = fmaf(zi, zi, nrm);
                 }
                 zi = 1.f;
+#pragma unroll 4
                 for (int i = r; i < qd - 1; ++i) {
-                    zi = -(e[i] / z[i + 1]) * zi;
+                    zi = -__fdividef(e[i], z[i + 1]) * zi;
                     z[i + 1] = zi;
                     nrm = fmaf(zi, zi, nrm);
                 }
                 z[r] = 1.f;
                 const float sc = rsqrtf(nrm);
                 if (nrm < 3.0e38f && sc > 0.f) {
+#pragma unroll 4
                     for (int i = 0; i < qd; ++i) z[i] *= sc;
                 } else {                                 // overflow guard (never seen): fall back to the twist basis vector
                     for (int i = 0; i < qd; ++i) z[i] = (i == r) ? 1.f : 0.f;
