@@ -1117,6 +1117,10 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
         tj = tid - ti * (ti + 1) / 2;
     }
     {
+        // Tiles with tj & 4 load (and keep) their two 4-column halves in swapped order: the column-part loads of 8 consecutive
+        // tiles then fall into 8 different 16-byte bank groups (2 tj, 2 tj + 2, ... alone cover only the even ones: ncu showed
+        // 52 % excess wavefronts on these loads, 18 % of the kernel's shared-memory traffic).
+        const int sw = (tj >> 2) & 1;
         float2 acc[8][4];
 #pragma unroll
         for (int aa = 0; aa < 8; ++aa)
@@ -1126,7 +1130,7 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
             const float *ra = Y + 8 * ti, *rb = Y + 8 * tj;      // (columns >= LDQ of the last tile read the next row: never stored)
             for (int nn = 0; nn < n; ++nn) {
                 const float4 a0 = *reinterpret_cast<const float4 *>(ra + nn * LDQ), a1 = *reinterpret_cast<const float4 *>(ra + nn * LDQ + 4);
-                const float4 b0 = *reinterpret_cast<const float4 *>(rb + nn * LDQ), b1 = *reinterpret_cast<const float4 *>(rb + nn * LDQ + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(rb + nn * LDQ + 4 * sw), b1 = *reinterpret_cast<const float4 *>(rb + nn * LDQ + 4 - 4 * sw);
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 const float2 c0 = make_float2(b0.x, b0.y), c1 = make_float2(b0.z, b0.w), c2 = make_float2(b1.x, b1.y), c3 = make_float2(b1.z, b1.w);
 #pragma unroll
@@ -1144,9 +1148,10 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
             for (int aa = 0; aa < 8; ++aa) {         // rows 8 ti + aa, columns 8 tj .. 8 tj + 7
                 const int i = 8 * ti + aa;
                 if (i < LDQ) {
-                    *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
-                    if (8 * tj + 4 < LDQ)
-                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
+                    if (8 * tj + 4 * sw < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4 * sw) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
+                    if (8 * tj + 4 - 4 * sw < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4 - 4 * sw) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
                 }
             }
 #pragma unroll
@@ -1155,7 +1160,10 @@ __global__ void __launch_bounds__(TT, NRC < ((QD + 3) / 4) ? 4 : 3) cov_tridiag_
                 if (j < LDQ) {
                     float cv[8];
 #pragma unroll
-                    for (int aa = 0; aa < 8; ++aa) cv[aa] = ((bb & 1) ? acc[aa][bb >> 1].y : acc[aa][bb >> 1].x) * inv_n;
+                    for (int aa = 0; aa < 8; ++aa) {
+                        const float2 pr = sw ? acc[aa][(bb >> 1) ^ 2] : acc[aa][bb >> 1];   // tile column bb -> register pair
+                        cv[aa] = ((bb & 1) ? pr.y : pr.x) * inv_n;
+                    }
                     *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti) = make_float4(cv[0], cv[1], cv[2], cv[3]);
                     if (8 * ti + 4 < LDQ) *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
                 }
@@ -1299,6 +1307,10 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
         tj = tid - ti * (ti + 1) / 2;
     }
     {
+        // Tiles with tj & 4 load (and keep) their two 4-column halves in swapped order: the column-part loads of 8 consecutive
+        // tiles then fall into 8 different 16-byte bank groups (2 tj, 2 tj + 2, ... alone cover only the even ones: ncu showed
+        // 52 % excess wavefronts on these loads, 18 % of the kernel's shared-memory traffic).
+        const int sw = (tj >> 2) & 1;
         float2 acc[8][4];
 #pragma unroll
         for (int aa = 0; aa < 8; ++aa)
@@ -1308,7 +1320,7 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
             const float *ra = Y + 8 * ti, *rb = Y + 8 * tj;      // (columns >= LDQ of the last tile read the next row: never stored)
             for (int nn = 0; nn < n; ++nn) {
                 const float4 a0 = *reinterpret_cast<const float4 *>(ra + nn * LDQ), a1 = *reinterpret_cast<const float4 *>(ra + nn * LDQ + 4);
-                const float4 b0 = *reinterpret_cast<const float4 *>(rb + nn * LDQ), b1 = *reinterpret_cast<const float4 *>(rb + nn * LDQ + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(rb + nn * LDQ + 4 * sw), b1 = *reinterpret_cast<const float4 *>(rb + nn * LDQ + 4 - 4 * sw);
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 const float2 c0 = make_float2(b0.x, b0.y), c1 = make_float2(b0.z, b0.w), c2 = make_float2(b1.x, b1.y), c3 = make_float2(b1.z, b1.w);
 #pragma unroll
@@ -1326,9 +1338,10 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
             for (int aa = 0; aa < 8; ++aa) {         // rows 8 ti + aa, columns 8 tj .. 8 tj + 7
                 const int i = 8 * ti + aa;
                 if (i < LDQ) {
-                    *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
-                    if (8 * tj + 4 < LDQ)
-                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
+                    if (8 * tj + 4 * sw < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4 * sw) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
+                    if (8 * tj + 4 - 4 * sw < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4 - 4 * sw) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
                 }
             }
 #pragma unroll
@@ -1337,7 +1350,10 @@ __global__ void __launch_bounds__(TT, 4) cov_tridiag4_kernel(const BayesArgs a) 
                 if (j < LDQ) {
                     float cv[8];
 #pragma unroll
-                    for (int aa = 0; aa < 8; ++aa) cv[aa] = ((bb & 1) ? acc[aa][bb >> 1].y : acc[aa][bb >> 1].x) * inv_n;
+                    for (int aa = 0; aa < 8; ++aa) {
+                        const float2 pr = sw ? acc[aa][(bb >> 1) ^ 2] : acc[aa][bb >> 1];   // tile column bb -> register pair
+                        cv[aa] = ((bb & 1) ? pr.y : pr.x) * inv_n;
+                    }
                     *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti) = make_float4(cv[0], cv[1], cv[2], cv[3]);
                     if (8 * ti + 4 < LDQ) *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
                 }
@@ -1522,6 +1538,10 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
         tj = tid - ti * (ti + 1) / 2;
     }
     {
+        // Tiles with tj & 4 load (and keep) their two 4-column halves in swapped order: the column-part loads of 8 consecutive
+        // tiles then fall into 8 different 16-byte bank groups (2 tj, 2 tj + 2, ... alone cover only the even ones: ncu showed
+        // 52 % excess wavefronts on these loads, 18 % of the kernel's shared-memory traffic).
+        const int sw = (tj >> 2) & 1;
         float2 acc[8][4];
 #pragma unroll
         for (int aa = 0; aa < 8; ++aa)
@@ -1531,7 +1551,7 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
             const float *ra = Yt + 8 * ti, *rb = Yt + 8 * tj;
             for (int j = 0; j < p; ++j) {
                 const float4 a0 = *reinterpret_cast<const float4 *>(ra + j * LDQ), a1 = *reinterpret_cast<const float4 *>(ra + j * LDQ + 4);
-                const float4 b0 = *reinterpret_cast<const float4 *>(rb + j * LDQ), b1 = *reinterpret_cast<const float4 *>(rb + j * LDQ + 4);
+                const float4 b0 = *reinterpret_cast<const float4 *>(rb + j * LDQ + 4 * sw), b1 = *reinterpret_cast<const float4 *>(rb + j * LDQ + 4 - 4 * sw);
                 const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                 const float2 c0 = make_float2(b0.x, b0.y), c1 = make_float2(b0.z, b0.w), c2 = make_float2(b1.x, b1.y), c3 = make_float2(b1.z, b1.w);
 #pragma unroll
@@ -1549,9 +1569,10 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
             for (int aa = 0; aa < 8; ++aa) {
                 const int i = 8 * ti + aa;
                 if (i < LDQ) {
-                    *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
-                    if (8 * tj + 4 < LDQ)
-                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
+                    if (8 * tj + 4 * sw < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4 * sw) = make_float4(acc[aa][0].x * inv_n, acc[aa][0].y * inv_n, acc[aa][1].x * inv_n, acc[aa][1].y * inv_n);
+                    if (8 * tj + 4 - 4 * sw < LDQ)
+                        *reinterpret_cast<float4 *>(A + i * LDQ + 8 * tj + 4 - 4 * sw) = make_float4(acc[aa][2].x * inv_n, acc[aa][2].y * inv_n, acc[aa][3].x * inv_n, acc[aa][3].y * inv_n);
                 }
             }
 #pragma unroll
@@ -1560,7 +1581,10 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
                 if (j < LDQ) {
                     float cv[8];
 #pragma unroll
-                    for (int aa = 0; aa < 8; ++aa) cv[aa] = ((bb & 1) ? acc[aa][bb >> 1].y : acc[aa][bb >> 1].x) * inv_n;
+                    for (int aa = 0; aa < 8; ++aa) {
+                        const float2 pr = sw ? acc[aa][(bb >> 1) ^ 2] : acc[aa][bb >> 1];   // tile column bb -> register pair
+                        cv[aa] = ((bb & 1) ? pr.y : pr.x) * inv_n;
+                    }
                     *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti) = make_float4(cv[0], cv[1], cv[2], cv[3]);
                     if (8 * ti + 4 < LDQ) *reinterpret_cast<float4 *>(A + j * LDQ + 8 * ti + 4) = make_float4(cv[4], cv[5], cv[6], cv[7]);
                 }
