@@ -85,3 +85,18 @@ def test_video_io_roundtrip_and_report(tmp_path):
     assert rep["Ave Rel. Error"] > 0 and np.isinf(rep["other_psnr"]) and abs(rep["our_psnr"] - 48.13) < 0.01
     with pytest.raises(FileNotFoundError):
         video_io.read_video_sequence(str(tmp_path / "none"))
+
+
+def test_graph_row_buckets_hold_the_draw_and_are_few():
+    """schedule._graph_rows: the row count of a captured round is one of ~10 buckets per step (cap, 3/4 cap, 1/2 cap, ...,
+    >= 512), never smaller than the rows the draw needs."""
+    from vnlb_b200.schedule import _graph_rows
+    cap = 16384
+    seen = set()
+    for need in list(range(1, 2000, 37)) + list(range(2000, cap + 1, 311)) + [cap]:
+        rows = _graph_rows(need, cap)
+        assert rows >= min(need, cap) and rows <= cap and rows >= 512
+        seen.add(rows)
+        if rows > 512 and rows * 3 // 4 >= 512:
+            assert need > rows * 3 // 4 or rows == 512 or need > rows // 2     # the next smaller bucket would not hold it
+    assert len(seen) <= 11
