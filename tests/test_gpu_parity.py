@@ -550,8 +550,19 @@ def test_bayes_gram_split_path_matches_single_kernel_and_oracle(vb, kind):
     assert np.abs(outs[1][0] - outs[0][0]).max() <= 2e-4 * np.abs(outs[0][0]).max()
 
 
-def test_bayes_large_call_is_chunked_consistently(vb):
-    """More groups than one workspace chunk (16384): every group of the big call equals the same group filtered in a small call."""
+@pytest.mark.parametrize("split", [1, 0])
+def test_bayes_large_call_is_chunked_consistently(vb, split):
+    """More groups than one workspace chunk (16384): every group of the big call equals the same group filtered in a small
+    call, bit for bit -- whichever chunk, block and warp rotation it falls in; split path and single-kernel path."""
+    from vnlb_b200 import _lib as L
+    prev = L.lib.vnlb_set_bayes_split(split)
+    try:
+        _chunk_consistency(vb)
+    finally:
+        L.lib.vnlb_set_bayes_split(prev)
+
+
+def _chunk_consistency(vb):
     from vnlb_b200 import deno
     from vnlb_b200.utils import AttrDict
     a_gpu = gargs(vb, 0)

@@ -162,11 +162,14 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int d = 16; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
     return v;
 }
-// block-wide reductions broadcast to every thread; `red` has 8 slots, `phase` alternates 0/1
+// block-wide reductions broadcast to every thread; `red` has 8 slots, `phase` alternates 0/1.  The partial sums are
+// stored and added in LOGICAL (rotated) warp order, so the result does not depend on warp_rotation(), i.e. on which
+// block a problem runs in.
+__device__ __forceinline__ int logical_warp() { return ((threadIdx.x >> 5) + warp_rotation()) & ((blockDim.x >> 5) - 1); }
 __device__ __forceinline__ float block_sum(float v, float *red, int &phase) {
     v = warp_sum(v);
     float *r = red + 4 * phase;
-    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+    if ((threadIdx.x & 31) == 0) r[logical_warp()] = v;
     __syncthreads();
     phase ^= 1;
     return (r[0] + r[1]) + (r[2] + r[3]);
@@ -174,7 +177,7 @@ __device__ __forceinline__ float block_sum(float v, float *red, int &phase) {
 __device__ __forceinline__ float block_max(float v, float *red, int &phase) {
     v = warp_max(v);
     float *r = red + 4 * phase;
-    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+    if ((threadIdx.x & 31) == 0) r[logical_warp()] = v;
     __syncthreads();
     phase ^= 1;
     return fmaxf(fmaxf(r[0], r[1]), fmaxf(r[2], r[3]));
