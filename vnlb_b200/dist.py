@@ -84,13 +84,14 @@ def make_layout(h, ps, world_size, halo, row_weights=None, margin=0):
     return bands, tiles
 
 
-def rebalanced_cuts(remaining_rows, speeds, bands, bands0, margin, ps):
+def rebalanced_cuts(remaining_rows, speeds, bands, bands0, margin, ps, damping=1.0):
     """New band borders from a progress report (host arithmetic, identical on every rank).
     remaining_rows [H]: reference pixels still masked per global row; speeds[r]: reference pixels rank r cleared per
     millisecond so far; bands: the current bands (who owns a row now); bands0: the bands the tiles were laid out for.
     A row's remaining time is its count over its owner's speed; the new borders cut the cumulated time into equal
     parts, each border kept within `margin` rows of bands0's border (the image rows a tile holds) and the bands kept
-    at least `ps` rows high.  Returns the list of new bands."""
+    at least `ps` rows high.  `damping` < 1 moves a border only that fraction of the predicted way (the early speed
+    estimate overshoots: measured 2.6 x at N = 2 after two rounds).  Returns the list of new bands."""
     rem = np.asarray(remaining_rows, np.float64)
     h = rem.shape[0]
     world = len(bands)
@@ -103,6 +104,8 @@ def rebalanced_cuts(remaining_rows, speeds, bands, bands0, margin, ps):
     for k in range(1, world):
         orig = bands0[k][0]
         b = int(np.searchsorted(cum, total * k / world)) + 1 if total > 0 else orig
+        cur = bands[k][0]
+        b = cur + int(round(damping * (b - cur)))          # damping < 1: move only part of the predicted way
         b = min(max(b, orig - margin), orig + margin)
         cuts.append(max(b, cuts[-1] + ps))
     cuts.append(h)
@@ -203,7 +206,8 @@ class BandRebalancer:
     moved strips in their CURRENT state.  The number of groups a band produces depends on its content (how widely
     the similar patches of a region spread), which is unknown before the step has run for a while."""
 
-    def __init__(self, bands, tiles, rank, group, margin, h, w, t, ps, pt, proc_step):
+    def __init__(self, bands, tiles, rank, group, margin, h, w, t, ps, pt, proc_step, damping=1.0):
+        self.damping = float(damping)
         self.bands0 = list(bands)                # borders may move within +-margin of THESE
         self.bands = list(bands)
         self.tiles, self.rank, self.group, self.margin = tiles, rank, group, margin
@@ -233,7 +237,7 @@ class BandRebalancer:
         v = vec.cpu().numpy().astype(np.float64)
         rem_rows, el, ini = v[:h], v[h:h + world], v[h + world:]
         speeds = [max(ini[r] - rem_rows[a:b].sum(), 1.0) / max(el[r], 1e-3) for r, (a, b) in enumerate(self.bands)]
-        new = rebalanced_cuts(rem_rows, speeds, self.bands, self.bands0, self.margin, self.ps)
+        new = rebalanced_cuts(rem_rows, speeds, self.bands, self.bands0, self.margin, self.ps, self.damping)
         self._migrate(mask, new)
         self.moved.append(dict(old=self.bands[rank], new=new[rank], elapsed_ms=[round(float(x), 2) for x in el],
                                speeds=[round(float(x), 1) for x in speeds]))
@@ -313,7 +317,7 @@ def _max_flow_y(flows, y0, y1):
 
 def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="default", params=None, stats=None,
                         group=None, device=None, clean=None, max_flow=None, row_weights=None, gather=True,
-                        rebalance=False, rebalance_round=2, margin_frac=0.10):
+                        rebalance=None, rebalance_round=None, margin_frac=0.10, rebalance_damping=None):
     """vnlb.denoise over all ranks of `group`.  Every rank passes the same `noisy` [T,C,H,W] (host, ideally pinned, or
     device) and the same `flows`; only its own band + halo rows are copied to its GPU.  Returns (deno, basic, seconds):
     the full frames on every rank (gather=True) or, with gather=False, this rank's band rows only as
@@ -324,12 +328,21 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
     row_weights : optional [H] expected cost per reference row for the initial band partition (None = equal row counts).
     rebalance : move the band borders once per step, after `rebalance_round` rounds, to equalise the predicted
                remaining time of the ranks (BandRebalancer); the tiles carry `margin_frac` x band rows of extra
-               margin on each side for that.  OFF by default: measured on 2 B200s (1920x1080x30, sigma 10) the early
-               speed estimate overshoots (bands 861 k / 808 k groups without, 792 k / 877 k with) and the call is slower
-               (1008 vs 882 ms); kept as an option for content whose cost per row is known to be skewed.
+               margin on each side for that.  OFF by default (None = environment VNLB_REBALANCE, else off): measured on
+               2 B200s (1920x1080x30, sigma 10) the early speed estimate overshoots (bands 861 k / 808 k groups
+               without, 792 k / 877 k after two rounds undamped: 1008 vs 882 ms); with `rebalance_round` = 6 and
+               `rebalance_damping` = 0.4 the bands end at 823 k / 845 k but the call is not faster (856 vs 851 ms):
+               kept as an option for content whose cost per row is known to be skewed.
     """
     clock = Timer()
     clock.tic()
+    import os
+    if rebalance is None:                      # experiments: VNLB_REBALANCE=1 [VNLB_REBALANCE_ROUND, VNLB_REBALANCE_DAMP]
+        rebalance = os.environ.get("VNLB_REBALANCE", "0") == "1"
+    if rebalance_round is None:
+        rebalance_round = int(os.environ.get("VNLB_REBALANCE_ROUND", "2"))
+    if rebalance_damping is None:
+        rebalance_damping = float(os.environ.get("VNLB_REBALANCE_DAMP", "1.0"))
     if schedule != "fast":
         raise ValueError("denoise_distributed runs the throughput schedule (the parity schedule replays the reference's "
                          "single-process random draws and has no multi-GPU meaning)")
@@ -369,7 +382,7 @@ def denoise_distributed(noisy, sigma, flows=None, schedule="fast", version="defa
         reb = None
         if rebalance:
             reb = BandRebalancer(bands, tiles, rank, group, margin, H, W, T, ps, int(params["sizePatchTime"][0]),
-                                 int(params["procStep"][0]))
+                                 int(params["procStep"][0]), rebalance_damping)
         cur = dict(bands=bands)
 
         def reduce_fn(images):
