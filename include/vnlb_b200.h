@@ -208,6 +208,10 @@ int vnlb_bayes_debug(float *pnoisy, const float *pbasic, const uint8_t *flat, co
  * results agree to rounding.  Returns the previous setting.  (Environment: VNLB_BAYES_SPLIT=0 at start-up.)
  * vnlb_bayes_workspace_bytes() follows the current setting. */
 int vnlb_set_bayes_split(int on);
+/* Wiener filter of the Bayes kernels on the tensor cores (3xTF32 mma.sync m16n8k8 for the two products of the filter)
+ * instead of FFMA2.  Same results to FP32 rounding; measured slower on B200, hence off by default.
+ * Returns the previous setting.  (Environment: VNLB_FILTER_MMA=1 at start-up.) */
+int vnlb_set_filter_mma(int on);
 
 /* Fusion of vpss.fill_patches (search.py:91-98) + exec_flat_areas
  * (flat_areas.py:16-34) + bayes_est.denoise (bayes_est.py:17-62) + agg_patches

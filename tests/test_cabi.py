@@ -58,6 +58,8 @@ def test_round_draw_rejects_bad_arguments_without_a_gpu():
     assert int(_lib.lib.vnlb_kernel_launches()) == n0
     prev = _lib.lib.vnlb_set_search_path(1)
     assert prev in (0, 1, 2) and _lib.lib.vnlb_set_search_path(prev) == 1
+    prev = _lib.lib.vnlb_set_filter_mma(1)
+    assert prev in (0, 1) and _lib.lib.vnlb_set_filter_mma(prev) == 1
 
 
 def test_switches_and_counters_without_a_gpu():

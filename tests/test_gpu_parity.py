@@ -938,3 +938,34 @@ def test_graph_rounds_match_eager_rounds(vb, sigma):
     for a, b_ in zip(out["graph"][2], out["eager"][2]):
         assert abs(a - b_) <= 0.03 * b_, out
     assert out["graph"][2][0] == out["graph2"][2][0], out                  # step 1 is bit-deterministic (step 2 reads float-atomic sums)
+
+
+@pytest.mark.parametrize("step", [0, 1])
+def test_tensor_core_filter_matches_the_ffma_filter_and_the_oracle(vb, step):
+    """vnlb_set_filter_mma(1): the two products of the Wiener filter as 3xTF32 mma.sync tiles.  Same filtered patches as
+    the FFMA2 filter to FP32 rounding (<= 2e-5 relative) and within 1e-4 of the oracle, texture and flat-mix stacks,
+    split path of both steps."""
+    from vnlb_b200 import _lib as L
+    from vnlb_b200 import deno
+    from vnlb_b200.utils import AttrDict
+    n = 100 if step == 0 else 60
+    rs = np.random.RandomState(41 + step)
+    pn = _stress_stack(rs, n, 7, 2, 600., b=6)
+    pb = pn.copy() if step == 1 else np.zeros_like(pn)
+    flat = np.zeros(pn.shape[0], bool)
+    a_gpu, a_cpu = gargs(vb, step), oargs(step)
+    outs = {}
+    prev = L.lib.vnlb_set_filter_mma(0)
+    try:
+        for mode in (0, 1):
+            L.lib.vnlb_set_filter_mma(mode)
+            patches = AttrDict(noisy=cu(pn), basic=cu(pb), flat=cu(flat.astype(np.uint8)))
+            deno.denoise(patches, a_gpu, "bayes")
+            outs[mode] = patches.noisy.cpu().numpy()
+    finally:
+        L.lib.vnlb_set_filter_mma(prev)
+    ref_n, _, _ = orc.bayes_denoise(pn, pb, flat, a_cpu)
+    for g in range(pn.shape[0]):
+        nrm = np.linalg.norm(ref_n[g])
+        assert np.linalg.norm(outs[1][g] - outs[0][g]) / nrm < 2e-5, g
+        assert np.linalg.norm(outs[1][g] - ref_n[g]) / nrm < 1e-4, g

@@ -37,7 +37,7 @@ EXPORTS = [
     "vnlb_last_error", "vnlb_version", "vnlb_rgb2yuv", "vnlb_yuv2rgb", "vnlb_init_mask", "vnlb_init_mask_tile",
     "vnlb_set_search_path", "vnlb_search_workspace_bytes", "vnlb_search_topk", "vnlb_fill_patches", "vnlb_mask_update",
     "vnlb_count_mask", "vnlb_select_queries", "vnlb_pad_queries", "vnlb_round_dedup", "vnlb_round_draw", "vnlb_round_dedup_dev",
-    "vnlb_flat_areas", "vnlb_bayes_workspace_bytes", "vnlb_bayes_filter", "vnlb_bayes_debug", "vnlb_bayes_matrix_dim", "vnlb_bayes_fused_supported", "vnlb_set_bayes_split", "vnlb_bayes_aggregate_fused", "vnlb_aggregate",
+    "vnlb_flat_areas", "vnlb_bayes_workspace_bytes", "vnlb_bayes_filter", "vnlb_bayes_debug", "vnlb_bayes_matrix_dim", "vnlb_bayes_fused_supported", "vnlb_set_bayes_split", "vnlb_set_filter_mma", "vnlb_bayes_aggregate_fused", "vnlb_aggregate",
     "vnlb_normalize",
 ]
 
@@ -78,6 +78,7 @@ lib.vnlb_bayes_debug.argtypes = [_vp, _vp, _vp, _vp, _i, ctypes.POINTER(BayesPar
 lib.vnlb_bayes_matrix_dim.argtypes = [ctypes.POINTER(BayesParams), ctypes.POINTER(ctypes.c_int)]
 lib.vnlb_bayes_fused_supported.argtypes = [ctypes.POINTER(BayesParams)]
 lib.vnlb_set_bayes_split.argtypes = [_i]
+lib.vnlb_set_filter_mma.argtypes = [_i]
 lib.vnlb_bayes_aggregate_fused.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, ctypes.POINTER(BayesParams), _f, _vp, _vp, _vp, _sz, _vp]
 lib.vnlb_aggregate.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]
 lib.vnlb_normalize.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _vp]

@@ -11,6 +11,7 @@ int bayes_matrix_dim(const VnlbBayesParams *p, int *is_gram);
 size_t bayes_workspace_bytes(int B, const VnlbBayesParams *p);
 bool bayes_tridiag_supported(const VnlbBayesParams *p);
 int set_bayes_split(int on);
+int set_filter_mma(int on);
 int launch_bayes_fused(const float *img_noisy, const float *img_basic, const long long *inds, int B, int T, int H,
                        int W, const VnlbBayesParams *p, float flat_thresh, float *deno, float *weights,
                        void *ws, size_t ws_bytes, cudaStream_t st);
@@ -73,6 +74,7 @@ extern "C" int vnlb_bayes_debug(float *pnoisy, const float *pbasic, const uint8_
 }
 
 extern "C" int vnlb_set_bayes_split(int on) { return set_bayes_split(on); }
+extern "C" int vnlb_set_filter_mma(int on) { return set_filter_mma(on); }
 
 extern "C" int vnlb_bayes_fused_supported(const VnlbBayesParams *p) { return p && bayes_tridiag_supported(p) ? 1 : 0; }
 

@@ -142,6 +142,7 @@ struct BayesArgs {
     float *ws;                     // split path: per-problem workspace (see cov_tridiag_kernel)
     int ws_stride;                 // floats per problem
     int ws_pitch;                  // floats per (d | e | tau) vector in the workspace
+    int filter_mma;                // Wiener filter on the tensor cores (3xTF32 mma.sync, filter_chunk_mma)
     VnlbBayesParams P;
     TriLayout L;
 };
@@ -235,6 +236,112 @@ __device__ __forceinline__ void filter_chunk(float *X, const float *Vt, const fl
             o0 = fmaf(zc[8 * b + 6], h.z, o0); o1 = fmaf(zc[8 * b + 7], h.w, o1);
         }
         if (on) xr[j] = (o0 + o1) + mean[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wiener filter on the tensor cores (VNLB_FILTER_MMA): the two products of the filter, Z = X V (rows x p x m) and
+// Xhat = (Z diag(coef)) V^T (rows x m x p), as mma.sync.m16n8k8 TF32 tiles with 3xTF32 operand splitting (a = hi + lo,
+// hi = cvt.rna.tf32(a), lo = cvt.rna.tf32(a - hi); d += hi hi + lo hi + hi lo: FP32-level accuracy).  filter_chunk is
+// bound by the shared-memory data pipe -- every thread streams the whole of Vt twice (4 MB LDS.128 per patch element for
+// 4 MB FFMA2 + 8 MB FFMA; ncu: 48 % of the kernel's shared-memory wavefronts); as mma fragments one 4-byte load per lane
+// feeds 128 / 256 multiply-adds.  A warp owns a tile of 16 patches (rows of X): Z stays in registers as accumulator
+// fragments, is scaled by the coefficients, and serves as the A operand of the second product with the K index
+// permuted (k-slot t <-> eigenpair 8 b + 2 t, slot t + 4 <-> 8 b + 2 t + 1), which is exactly the accumulator layout;
+// B then is one 8-byte load of Vt[j][8 b + 2 t .. + 1].  Same X / Vt / coef / mean layout as filter_chunk.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int MB>
+__device__ __forceinline__ void filter_chunk_mma(float *X, const float *Vt, const float *coef, const float *mean, int rows,
+                                                 int p, int XS, int m, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int rt = warp; rt * 16 < rows; rt += TT / 32) {
+        const int r0 = rt * 16 + g, r1 = r0 + 8;
+        const bool ok0 = r0 < rows, ok1 = r1 < rows;
+        float *x0 = X + min(r0, rows - 1) * XS, *x1 = X + min(r1, rows - 1) * XS;   // rows beyond the chunk: read row rows-1, never stored
+        float z[MB][4], zx[MB][4];               // hi x hi products / cross terms: two independent mma chains per tile
+#pragma unroll
+        for (int b = 0; b < MB; ++b) {
+            z[b][0] = 0.f; z[b][1] = 0.f; z[b][2] = 0.f; z[b][3] = 0.f;
+            zx[b][0] = 0.f; zx[b][1] = 0.f; zx[b][2] = 0.f; zx[b][3] = 0.f;
+        }
+        // ---- Z = X V
+#pragma unroll 2
+        for (int k0 = 0; k0 < p; k0 += 8) {
+            const int ka = k0 + t, kb = k0 + t + 4;
+            const bool va = ka < p, vb = kb < p;
+            uint32_t ah[4], al[4];
+            tf32_split(va ? x0[ka] : 0.f, ah[0], al[0]);
+            tf32_split(va ? x1[ka] : 0.f, ah[1], al[1]);
+            tf32_split(vb ? x0[kb] : 0.f, ah[2], al[2]);
+            tf32_split(vb ? x1[kb] : 0.f, ah[3], al[3]);
+#pragma unroll
+            for (int b = 0; b < MB; ++b) {
+                uint32_t bh[2], bl[2];
+                tf32_split(va ? Vt[ka * MR + 8 * b + g] : 0.f, bh[0], bl[0]);
+                tf32_split(vb ? Vt[kb * MR + 8 * b + g] : 0.f, bh[1], bl[1]);
+                mma_tf32(zx[b], al, bh);
+                mma_tf32(z[b], ah, bh);
+                mma_tf32(zx[b], ah, bl);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < MB; ++b) { z[b][0] += zx[b][0]; z[b][1] += zx[b][1]; z[b][2] += zx[b][2]; z[b][3] += zx[b][3]; }
+        // ---- scale by the Wiener coefficients; accumulator layout = A layout of the second product (permuted K)
+        uint32_t zh[MB][4], zl[MB][4];
+#pragma unroll
+        for (int b = 0; b < MB; ++b) {
+            const int ra = 8 * b + 2 * t;
+            const float c0 = ra < m ? coef[ra] : 0.f, c1 = ra + 1 < m ? coef[ra + 1] : 0.f;
+            tf32_split(z[b][0] * c0, zh[b][0], zl[b][0]);   // (row g,     k-slot t)
+            tf32_split(z[b][2] * c0, zh[b][1], zl[b][1]);   // (row g + 8, k-slot t)
+            tf32_split(z[b][1] * c1, zh[b][2], zl[b][2]);   // (row g,     k-slot t + 4)
+            tf32_split(z[b][3] * c1, zh[b][3], zl[b][3]);   // (row g + 8, k-slot t + 4)
+        }
+        // ---- Xhat = Zc V^T + mean, written over X
+#pragma unroll 2
+        for (int j0 = 0; j0 < p; j0 += 8) {
+            const int jn = j0 + g;
+            float o[4] = {0.f, 0.f, 0.f, 0.f}, ox[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int b = 0; b < MB; ++b) {
+                float2 v2 = make_float2(0.f, 0.f);
+                if (jn < p) v2 = *reinterpret_cast<const float2 *>(Vt + jn * MR + 8 * b + 2 * t);
+                uint32_t bh[2], bl[2];
+                tf32_split(v2.x, bh[0], bl[0]);
+                tf32_split(v2.y, bh[1], bl[1]);
+                mma_tf32(ox, zl[b], bh);
+                mma_tf32(o, zh[b], bh);
+                mma_tf32(ox, zh[b], bl);
+            }
+            o[0] += ox[0]; o[1] += ox[1]; o[2] += ox[2]; o[3] += ox[3];
+            const int jc = j0 + 2 * t;
+            if (jc < p) {
+                const float mj = mean[jc];
+                if (ok0) x0[jc] = o[0] + mj;
+                if (ok1) x1[jc] = o[2] + mj;
+            }
+            if (jc + 1 < p) {
+                const float mj = mean[jc + 1];
+                if (ok0) x0[jc + 1] = o[1] + mj;
+                if (ok1) x1[jc + 1] = o[3] + mj;
+            }
+        }
     }
 }
 
@@ -2436,6 +2543,15 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 }
             }
             __syncthreads();
+            if (a.filter_mma && m > 0) {
+                switch ((m + 7) >> 3) {
+                    case 1: filter_chunk_mma<1>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                    case 2: filter_chunk_mma<2>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                    case 3: filter_chunk_mma<3>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                    case 4: filter_chunk_mma<4>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                    default: filter_chunk_mma<5>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                }
+            } else
             switch ((m + 7) >> 3) {
                 case 0: filter_chunk<0>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
                 case 1: filter_chunk<1>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
@@ -2515,11 +2631,26 @@ size_t bayes_workspace_bytes(int B, const VnlbBayesParams *p) {
     return (size_t)(B < SPLIT_CHUNK ? B : SPLIT_CHUNK) * split_bytes_per_group(L, p->c);
 }
 
+// Wiener filter on the tensor cores (filter_chunk_mma): VNLB_FILTER_MMA=1 in the environment or vnlb_set_filter_mma(1).
+// Parity-green and measured SLOWER than the FFMA2 filter (15.31 vs 14.40 ms and 9.21 vs 8.35 ms per 16384 groups:
+// mma.sync TF32 issues at 0.5 per cycle and SM on this part and every operand needs its 3xTF32 split): off by default.
+static int g_filter_mma = -1;
+static int filter_mma_setting() {
+    if (g_filter_mma < 0) { const char *e = getenv("VNLB_FILTER_MMA"); g_filter_mma = (e && e[0] == '1') ? 1 : 0; }
+    return g_filter_mma;
+}
+int set_filter_mma(int on) {
+    const int prev = filter_mma_setting();
+    g_filter_mma = on ? 1 : 0;
+    return prev;
+}
+
 template <bool FUSED>
 static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_t st);
 
 template <bool FUSED>
 static int launch_bayes_any(BayesArgs &a, int B, const char *what, void *ws, size_t ws_bytes, cudaStream_t st) {
+    a.filter_mma = filter_mma_setting();
     if (!use_split(a.L)) return launch_bayes_chunk<FUSED>(a, B, what, st);
     const VnlbBayesParams &P = a.P;
     const size_t per_group = split_bytes_per_group(a.L, P.c);
