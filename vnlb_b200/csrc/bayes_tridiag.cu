@@ -1756,7 +1756,9 @@ __global__ void __launch_bounds__(64, 8) gram_tridiag_kernel(const BayesArgs a) 
 }
 
 // SPLIT: phases 0-1 were done by cov_tridiag_kernel; (d, e, tau, mean, packed reflectors) come from the workspace.
-template <bool FUSED, bool GRAM, bool SPLIT>
+// MMA: the Wiener filter on the tensor cores (filter_chunk_mma); its own instantiation, so that the default kernels carry
+// none of its code (registers, instruction cache)
+template <bool FUSED, bool GRAM, bool SPLIT, bool MMA = false>
 __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs a) {
     constexpr int NT = GRAM ? 1 : 3;               // 4x4 tiles of the (covariance | Gram) matrix per thread
     extern __shared__ __align__(16) float sm[];
@@ -2543,15 +2545,20 @@ __global__ void __launch_bounds__(TT, GRAM ? 7 : 5) bayes_kernel(const BayesArgs
                 }
             }
             __syncthreads();
-            if (a.filter_mma && m > 0) {
-                switch ((m + 7) >> 3) {
-                    case 1: filter_chunk_mma<1>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
-                    case 2: filter_chunk_mma<2>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
-                    case 3: filter_chunk_mma<3>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
-                    case 4: filter_chunk_mma<4>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
-                    default: filter_chunk_mma<5>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+            bool filtered = false;
+            if constexpr (MMA) {
+                if (m > 0) {
+                    switch ((m + 7) >> 3) {
+                        case 1: filter_chunk_mma<1>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                        case 2: filter_chunk_mma<2>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                        case 3: filter_chunk_mma<3>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                        case 4: filter_chunk_mma<4>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                        default: filter_chunk_mma<5>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
+                    }
+                    filtered = true;
                 }
-            } else
+            }
+            if (!filtered)
             switch ((m + 7) >> 3) {
                 case 0: filter_chunk<0>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
                 case 1: filter_chunk<1>(X, Vt, coef, mean, rows, p, XS, m, tid); break;
@@ -2697,7 +2704,7 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         auto k1 = g_tail2 ? gram_tridiag_kernel<FUSED, QD, true> : gram_tridiag_kernel<FUSED, QD, false>;
         auto k1c = tridiag_tail_kernel<QD, SPLIT_NR3, 2, 32, 16, GRAM_PITCH, 3 * GRAM_PITCH + 100, gram_trail_off<QD>(100), 0>;
         const size_t smem1c = (size_t)tridiag_scratch_floats<QD, SPLIT_NR3, 2>() * sizeof(float);
-        auto k2 = bayes_kernel<FUSED, true, true>;
+        auto k2 = a.filter_mma ? bayes_kernel<FUSED, true, true, true> : bayes_kernel<FUSED, true, true, false>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
@@ -2735,7 +2742,7 @@ static int launch_bayes_chunk(BayesArgs &a, int B, const char *what, cudaStream_
         auto k1c = tridiag_tail_kernel<QD, SPLIT_NR3, 2, 32, 16, LDG, 4 * LDG, split_trail2_off<QD>(), 0>;
         const size_t smem1b = (size_t)tridiag_scratch_floats<QD, SPLIT_NR2, SPLIT_NR3>() * sizeof(float);
         const size_t smem1c = (size_t)tridiag_scratch_floats<QD, SPLIT_NR3, 2>() * sizeof(float);
-        auto k2 = bayes_kernel<FUSED, false, true>;
+        auto k2 = a.filter_mma ? bayes_kernel<FUSED, false, true, true> : bayes_kernel<FUSED, false, true, false>;
         e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return VNLB_ERR_CUDA; }
