@@ -8,16 +8,20 @@
 //   dist = 0; for c, ht, hy, hx:  d = q - cand;  dist = fmaf(d, d, dist)
 //   top-k ascending by (dist, candidate enumeration order frame -> y -> x)
 //
-// One CTA per query.  Two distance paths produce identical bits:
+// One CTA per query.  Three distance paths produce identical bits:
 //   * generic  : any (ps, pt, w_s), candidates strided over threads, operands
 //                read through L1/L2;
-//   * tiled    : ps=7, pt=2, w_s=27 (the classic VNLB setting): frame tiles
-//                staged in shared memory with cp.async, each lane owns a
-//                column of 9 candidates, the query patch lives in registers.
-// Selection: 4-pass radix select on the distance bits in shared memory, tie
-// resolution by enumeration order, bitonic sort of the k survivors.
+//   * tiled    : ps=7, pt=2, w_s=27, any number of frames: frame tiles staged in
+//                shared memory with cp.async in chunks of 3 frames, each lane owns
+//                a column of 9 candidates, the query plane lives in registers;
+//   * quad     : the same shape with at most 13 frames (the production setting):
+//                all frames of a phase resident, a lane owns 4 x 9 candidates for
+//                the whole query, distances stay in registers (search_quad_kernel).
+// Selection: quad kernel -- two histograms over the register-resident distances,
+// survivors ranked by counting (select_topk_regs); other kernels and the fallback
+// -- sample pivot or 4-pass radix select on the distances in shared memory, tie
+// resolution by enumeration order, bitonic sort of the survivors (select_topk).
 #include <stdlib.h>
-#include <string.h>
 
 #include "common.cuh"
 
